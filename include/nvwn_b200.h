@@ -1,0 +1,88 @@
+/*
+ * nvwn_b200.h -- handle-based C-ABI of the B200 WaveNet inference engine.
+ *
+ * One entry point per public member of the reference's host class
+ * nvWavenetInfer<T_weight,T_data,R,S,A> (nv_wavenet.cuh:220-640), so that the C++ facade
+ * (include/nv_wavenet.hpp), the reference C-ABI (include/wavenet_infer.h) and any FFI
+ * (ctypes, cgo, JNI ...) can drive the same engine.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a cudaError_t (>0) or a negative NVWN_E* code on
+ *     failure; nvwn_last_error() gives the message (thread-local).
+ *   - every float* / int* data argument may be host or device memory (cudaMemcpyDefault),
+ *     like the reference setters (nv_wavenet.cuh:285-308); data is copied before return.
+ *   - matrices fp32 column-major M x K; embeddings [A][R]; Lh float[N][L][B][2R];
+ *     selectors float[N][B]; yOut int[B][N]  (nv_wavenet.cuh:144, singleblock.cuh:232,245).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef NVWN_B200_H
+#define NVWN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nvwn_engine nvwn_engine;
+
+enum { NVWN_FP32 = 0, NVWN_FP16 = 1 };          /* T_data=float / T_data=half of the reference */
+enum { NVWN_EINVAL = -1, NVWN_EUNSUPPORTED = -2, NVWN_ENOMEM = -3 };
+/* kernel selection; the reference's Implementation enum values 0..4 are accepted and map to AUTO */
+enum { NVWN_KERNEL_AUTO = 0, NVWN_KERNEL_STREAM = 16, NVWN_KERNEL_TENSORCORE = 17 };
+
+/* nvWavenetInfer::nvWavenetInfer (nv_wavenet.cuh:311) */
+int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layers, int max_dilation,
+                int batch_size, int num_samples, int impl, int tanh_embed);
+/* nvWavenetInfer::~nvWavenetInfer (nv_wavenet.cuh:362-395) */
+int nvwn_destroy(nvwn_engine* e);
+const char* nvwn_last_error(void);
+
+/* nv_wavenet.cuh:396-415 */
+int nvwn_set_embeddings(nvwn_engine* e, const float* embedPrev, const float* embedCur);
+int nvwn_set_layer_weights(nvwn_engine* e, int layer, const float* Wprev, const float* Wcur, const float* Bh,
+                           const float* Wres, const float* Bres, const float* Wskip, const float* Bskip);
+int nvwn_set_out_weights(nvwn_engine* e, const float* Wzs, const float* Bzs, const float* Wza, const float* Bza);
+/* nv_wavenet.cuh:417-422: resets the feedback history to 128/128, copies Lh and selectors */
+int nvwn_set_inputs(nvwn_engine* e, const float* Lh, const float* selectors);
+/* extension: selectors only / conditioning only (conditioning may be uploaded in chunks of whole samples) */
+int nvwn_set_selectors(nvwn_engine* e, const float* selectors);
+int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int num_samples, void* stream);
+int nvwn_reset_history(nvwn_engine* e);
+/* extension (teacher forcing): forced[b*num_samples + t] is fed back instead of the sampled index;
+ * NULL switches it off.  Copied. */
+int nvwn_set_forced(nvwn_engine* e, const int* forced);
+/* extension: replicate rank `root`'s packed weights to every rank's engine is done by the caller
+ * (NCCL broadcast of the blob below); these expose the packed device blob. */
+int nvwn_weight_blob(nvwn_engine* e, void** dev_ptr, unsigned long long* bytes);
+/* must be called after the blob was overwritten (e.g. by an NCCL broadcast) */
+int nvwn_weights_updated(nvwn_engine* e);
+
+/* nv_wavenet.cuh:499-639.  run_partial generates samples [init_sample, init_sample+count) of a
+ * num_samples-long utterance batch; yOut (optional, host or device) receives the whole int[B][N]. */
+int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples, int batch_size,
+                     int* yOut, int dump_activations, void* stream);
+int nvwn_run(nvwn_engine* e, int num_samples, int batch_size, int* yOut, int dump_activations, void* stream);
+/* nv_wavenet.cuh:439-444: 2-D copy of yOut[b][offset .. offset+size) for every b */
+int nvwn_get_yout(nvwn_engine* e, int* yOut, int offset, int size, void* stream);
+
+/* last-sample activations [B][dim] as fp32 (nv_wavenet.cuh:424-438); valid after a run with dump=1 */
+int nvwn_get_xt_out(nvwn_engine* e, int layer, float* out);
+int nvwn_get_skip_out(nvwn_engine* e, int layer, float* out);
+int nvwn_get_zs(nvwn_engine* e, float* out);
+int nvwn_get_za(nvwn_engine* e, float* out);
+int nvwn_get_p(nvwn_engine* e, float* out);
+
+/* introspection: what the last launch used */
+typedef struct {
+    int kernel;            /* NVWN_KERNEL_STREAM / NVWN_KERNEL_TENSORCORE */
+    int grid, block, smem_bytes, batch_per_cta, cluster;
+    unsigned long long launches;        /* kernel launches issued by this engine so far */
+    unsigned long long weight_bytes;    /* algorithmic weight+bias bytes per utterance-sample */
+} nvwn_launch_info;
+int nvwn_get_launch_info(nvwn_engine* e, nvwn_launch_info* info);
+int nvwn_device_count(void);
+int nvwn_set_device(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

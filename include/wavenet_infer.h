@@ -1,0 +1,61 @@
+/*
+ * wavenet_infer.h -- the reference's C-ABI for the WaveNet inference hot path, kept verbatim
+ * in meaning so that libwavenet_infer.so built from this repo is a drop-in for the one built
+ * by the reference (replaces pytorch/wavenet_infer.h:28-58 / pytorch/wavenet_infer.cu:105-149).
+ *
+ * Semantics kept from the reference (pytorch/wavenet_infer.cu:40-145):
+ *   - R/S/A are fixed at build time: R=64, S=256, A=256, arithmetic in fp32
+ *     (typedef nvWavenetInfer<float,float,R,S,A>, wavenet_infer.cu:35-38);
+ *   - every float* may point to host or device memory and is copied before return;
+ *     the float** arguments are host arrays of num_layers pointers;
+ *   - all matrices fp32 column-major M x K (README.md:38); embeddings A x R as emb[a*R + r];
+ *   - cond_input is float[sample_count][num_layers][batch_size][2R];
+ *   - output-layer biases are zero (wavenet_infer.cu:75-82);
+ *   - output selectors are drawn on the host with libc rand(), two draws per element,
+ *     batch-major, value = rand()/RAND_MAX  (Matrix::randomize(0.5, 1.0), wavenet_infer.cu:92-93,
+ *     matrix.cpp:38-56) -- so a caller that seeds srand() gets the reference's selectors;
+ *   - samples is caller-allocated int[batch_size][sample_count], host OR device;
+ *   - synchronous; CUDA failures print "GPUassert: ..." to stderr and exit(code)
+ *     (nv_wavenet_util.cuh:34-40);
+ *   - `implementation` 0..4 (AUTO, SINGLE_BLOCK, DUAL_BLOCK, PERSISTENT, MANYBLOCK) is accepted
+ *     and ignored: one sm_100a kernel family replaces all four.
+ *
+ * The arithmetic of this entry point is bit-exact fp32.  Set the environment
+ * variable NVWN_PRECISION=fp16 to route it through the fp16 tensor-core kernel instead.
+ */
+#ifndef WAVENET_INFER_H
+#define WAVENET_INFER_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void wavenet_infer(int sample_count,
+                   int batch_size,
+                   float* embedding_prev,
+                   float* embedding_curr,
+                   int num_layers,
+                   int max_dilation,
+                   float** in_layer_weights_prev,
+                   float** in_layer_weights_curr,
+                   float** in_layer_biases,
+                   float** res_layer_weights,
+                   float** res_layer_biases,
+                   float** skip_layer_weights,
+                   float** skip_layer_biases,
+                   float* conv_out_weight,
+                   float* conv_end_weight,
+                   int use_embed_tanh,
+                   float* cond_input,
+                   int implementation,
+                   int* samples);
+
+/* channel counts of this build (pytorch/wavenet_infer.h:54-57) */
+int get_R(void);
+int get_S(void);
+int get_A(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

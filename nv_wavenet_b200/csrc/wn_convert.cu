@@ -1,0 +1,45 @@
+// wn_convert.cu -- dtype conversion / fill helpers (replaces nv_wavenet_conversions.cuh:28-116).
+#include "wn_common.h"
+
+namespace {
+__global__ void f32_to_f16_kernel(__half* __restrict__ dst, const float* __restrict__ src, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // 4 elements per thread per trip when aligned
+    const size_t n4 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) ? n / 4 : 0;
+    for (size_t j = i; j < n4; j += stride) {
+        const float4 v = reinterpret_cast<const float4*>(src)[j];
+        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<unsigned*>(&lo);
+        o.y = *reinterpret_cast<unsigned*>(&hi);
+        reinterpret_cast<uint2*>(dst)[j] = o;
+    }
+    for (size_t j = n4 * 4 + i; j < n; j += stride) dst[j] = __float2half_rn(src[j]);
+}
+__global__ void fill_int_kernel(int* dst, int v, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+}  // namespace
+
+cudaError_t wn_f32_to_f16(__half* dst, const float* src_dev, size_t n, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    const int threads = 256;
+    size_t blocks = (n / 4 + threads - 1) / threads;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    f32_to_f16_kernel<<<(unsigned)blocks, threads, 0, stream>>>(dst, src_dev, n);
+    return cudaGetLastError();
+}
+
+cudaError_t wn_fill_int(int* dst, int value, size_t n, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    fill_int_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dst, value, n);
+    return cudaGetLastError();
+}

@@ -1,0 +1,403 @@
+// wn_engine.cu -- host side of the B200 WaveNet inference engine + the handle C-ABI (include/nvwn_b200.h).
+//
+// Owns every device buffer, uploads / converts weights and inputs, picks the kernel and launches it.
+// Re-design of the reference host class nvWavenetInfer<T_weight,T_data,R,S,A> (nv_wavenet.cuh:220-640):
+//   * all weights live in ONE packed device blob (so a multi-GPU job broadcasts it with a single NCCL call);
+//   * fp32 -> fp16 conversion runs on the device from a pinned/device staging area, asynchronously;
+//   * every buffer is freed; pointer kinds are detected with cudaPointerGetAttributes().type
+//     (the reference's attributes.memoryType no longer compiles, nv_wavenet_conversions.cuh:41);
+//   * yOut copies use cudaMemcpyDefault, so `samples` may be host or device memory.
+#include "../../include/nvwn_b200.h"
+#include "wn_common.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image, cudaStream_t stream, WnLaunchInfo* info);   // wn_tc_kernel.cu
+bool wn_tc_supported(int R, int S, int A, int L, int B);
+size_t wn_tc_image_bytes(int R, int S, int A, int L);
+cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream);
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t _e = (call);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail((int)_e, std::string(cudaGetErrorString(_e)) + " at " __FILE__ ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool is_device_ptr(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct nvwn_engine {
+    int dtype, R, S, A, L, maxDil, B, N, impl, tanhEmbed, device;
+    size_t td;                               // sizeof(TD)
+
+    // packed weight blob (TD elements), offsets in bytes
+    char* blob = nullptr;
+    size_t blob_bytes = 0;
+    size_t o_embPrev, o_embCur, o_Wprev, o_Wcur, o_Wres, o_Wskip, o_Wzs, o_Wza, o_Bh, o_Bres, o_Bskip, o_Bzs, o_Bza;
+
+    void* Lh = nullptr;                      // TD [N][L][B][2R]
+    float* sel = nullptr;                    // [N][B]
+    int* forced = nullptr;                   // [B][N]
+    bool use_forced = false;
+    int *yPrev = nullptr, *yCur = nullptr, *yOut = nullptr;
+    void* ring = nullptr;
+    float *xtOut = nullptr, *skipOut = nullptr, *Zs = nullptr, *Za = nullptr, *P = nullptr;
+
+    float* stage_dev = nullptr;              // device fp32 staging for host->fp16 uploads
+    size_t stage_elems = 0;
+
+    void* tc_image = nullptr;                // tensor-core kernel's pre-tiled weight image
+    bool tc_dirty = true;
+
+    WnLaunchInfo last{};
+    unsigned long long launches = 0;
+
+    template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(blob + off); }
+};
+
+namespace {
+
+// dst (TD, device) <- src (fp32, host or device), n elements
+int upload(nvwn_engine* e, void* dst, const float* src, size_t n, cudaStream_t stream = 0)
+{
+    if (n == 0) return 0;
+    if (e->dtype == NVWN_FP32) {
+        CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDefault, stream));
+        return 0;
+    }
+    if (is_device_ptr(src)) {
+        CK(wn_f32_to_f16(static_cast<__half*>(dst), src, n, stream));
+        return 0;
+    }
+    // host source: bounce through the device staging buffer in chunks
+    size_t done = 0;
+    while (done < n) {
+        const size_t m = (n - done < e->stage_elems) ? n - done : e->stage_elems;
+        CK(cudaMemcpyAsync(e->stage_dev, src + done, m * sizeof(float), cudaMemcpyHostToDevice, stream));
+        CK(wn_f32_to_f16(static_cast<__half*>(dst) + done, e->stage_dev, m, stream));
+        done += m;
+    }
+    return 0;
+}
+
+// dst (fp32, host or device) <- src (fp32 device)
+int download(float* dst, const float* src, size_t n)
+{
+    CK(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDefault));
+    return 0;
+}
+
+bool want_tc(const nvwn_engine* e, int batch)
+{
+    if (e->dtype != NVWN_FP16) return false;
+    if (e->impl == NVWN_KERNEL_STREAM) return false;
+    if (const char* env = getenv("NVWN_FP16_KERNEL")) {
+        if (!strcmp(env, "stream")) return false;
+    }
+    return wn_tc_supported(e->R, e->S, e->A, e->L, batch);
+}
+
+void fill_params(const nvwn_engine* e, WnParams& p, int init_sample, int count, int num_samples, int batch, int dump)
+{
+    memset(&p, 0, sizeof p);
+    p.L = e->L; p.R = e->R; p.S = e->S; p.A = e->A; p.maxDil = e->maxDil;
+    p.B = batch; p.N = num_samples; p.init_sample = init_sample; p.count = count;
+    p.tanhEmbed = e->tanhEmbed; p.dump = dump;
+    p.embPrev = e->blob + e->o_embPrev; p.embCur = e->blob + e->o_embCur;
+    p.Wprev = e->blob + e->o_Wprev; p.Wcur = e->blob + e->o_Wcur; p.Wres = e->blob + e->o_Wres; p.Wskip = e->blob + e->o_Wskip;
+    p.Wzs = e->blob + e->o_Wzs; p.Wza = e->blob + e->o_Wza;
+    p.Bh = e->blob + e->o_Bh; p.Bres = e->blob + e->o_Bres; p.Bskip = e->blob + e->o_Bskip; p.Bzs = e->blob + e->o_Bzs; p.Bza = e->blob + e->o_Bza;
+    p.Lh = e->Lh; p.sel = e->sel; p.forced = e->use_forced ? e->forced : nullptr;
+    p.yPrev = e->yPrev; p.yCur = e->yCur; p.ring = e->ring; p.yOut = e->yOut;
+    p.xtOut = e->xtOut; p.skipOut = e->skipOut; p.Zs = e->Zs; p.Za = e->Za; p.P = e->P;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nvwn_last_error(void) { return g_err.c_str(); }
+
+int nvwn_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int nvwn_set_device(int device)
+{
+    CK(cudaSetDevice(device));
+    return 0;
+}
+
+int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layers, int max_dilation,
+                int batch_size, int num_samples, int impl, int tanh_embed)
+{
+    if (!out) return fail(NVWN_EINVAL, "nvwn_create: out is NULL");
+    *out = nullptr;
+    if (dtype != NVWN_FP32 && dtype != NVWN_FP16) return fail(NVWN_EINVAL, "nvwn_create: dtype must be NVWN_FP32 or NVWN_FP16");
+    if (num_layers < 1 || max_dilation < 1 || batch_size < 1 || num_samples < 1) return fail(NVWN_EINVAL, "nvwn_create: sizes must be positive");
+    if (!wn_stream_supported(R, S, A, dtype == NVWN_FP16))
+        return fail(NVWN_EUNSUPPORTED, "nvwn_create: unsupported channel counts (R,S) must be one of (32,128) (64,128) (64,256) (128,256); A a multiple of 32");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(NVWN_EUNSUPPORTED, "nvwn_create: no CUDA device (this engine has no CPU fallback)");
+    }
+    nvwn_engine* e = new nvwn_engine();
+    e->dtype = dtype; e->R = R; e->S = S; e->A = A; e->L = num_layers; e->maxDil = max_dilation;
+    e->B = batch_size; e->N = num_samples; e->impl = impl; e->tanhEmbed = tanh_embed ? 1 : 0;
+    e->td = dtype == NVWN_FP16 ? 2 : 4;
+    cudaGetDevice(&e->device);
+
+    const size_t L = num_layers, td = e->td;
+    size_t off = 0;
+    auto take = [&](size_t elems) { size_t o = off; off = align_up(off + elems * td, 256); return o; };
+    e->o_embPrev = take((size_t)A * R); e->o_embCur = take((size_t)A * R);
+    e->o_Wprev = take(L * 2 * R * R); e->o_Wcur = take(L * 2 * R * R);
+    e->o_Wres = take(L * R * R); e->o_Wskip = take(L * S * R);
+    e->o_Wzs = take((size_t)A * S); e->o_Wza = take((size_t)A * A);
+    e->o_Bh = take(L * 2 * R); e->o_Bres = take(L * R); e->o_Bskip = take(L * S);
+    e->o_Bzs = take(A); e->o_Bza = take(A);
+    e->blob_bytes = off;
+
+    const size_t Bz = batch_size, Nz = num_samples;
+    e->stage_elems = dtype == NVWN_FP16 ? ((size_t)16 << 20) : 0;      // 64 MB of fp32 staging
+#define ALLOC(ptr, bytes)                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                                 \
+        if (_e != cudaSuccess) {                                                              \
+            int rc = fail((int)_e, std::string("cudaMalloc(" #ptr "): ") + cudaGetErrorString(_e)); \
+            nvwn_destroy(e);                                                                  \
+            return rc;                                                                        \
+        }                                                                                     \
+    } while (0)
+    ALLOC(e->blob, e->blob_bytes);
+    ALLOC(e->Lh, Nz * L * Bz * 2 * R * td);
+    ALLOC(e->sel, Nz * Bz * sizeof(float));
+    ALLOC(e->forced, Nz * Bz * sizeof(int));
+    ALLOC(e->yPrev, Bz * sizeof(int));
+    ALLOC(e->yCur, Bz * sizeof(int));
+    ALLOC(e->yOut, Nz * Bz * sizeof(int));
+    ALLOC(e->ring, (size_t)(max_dilation + 1) * L * Bz * R * td);
+    ALLOC(e->xtOut, L * Bz * R * sizeof(float));
+    ALLOC(e->skipOut, L * Bz * S * sizeof(float));
+    ALLOC(e->Zs, Bz * A * sizeof(float));
+    ALLOC(e->Za, Bz * A * sizeof(float));
+    ALLOC(e->P, Bz * A * sizeof(float));
+    if (e->stage_elems) ALLOC(e->stage_dev, e->stage_elems * sizeof(float));
+    if (dtype == NVWN_FP16 && wn_tc_supported(R, S, A, num_layers, batch_size)) ALLOC(e->tc_image, wn_tc_image_bytes(R, S, A, num_layers));
+#undef ALLOC
+    cudaMemsetAsync(e->blob, 0, e->blob_bytes, 0);
+    cudaMemsetAsync(e->yOut, 0, Nz * Bz * sizeof(int), 0);
+    cudaMemsetAsync(e->ring, 0, (size_t)(max_dilation + 1) * L * Bz * R * td, 0);
+    wn_fill_int(e->yPrev, 128, Bz, 0);
+    wn_fill_int(e->yCur, 128, Bz, 0);
+    cudaError_t se = cudaDeviceSynchronize();
+    if (se != cudaSuccess) { int rc = fail((int)se, cudaGetErrorString(se)); nvwn_destroy(e); return rc; }
+    *out = e;
+    return 0;
+}
+
+int nvwn_destroy(nvwn_engine* e)
+{
+    if (!e) return 0;
+    void* ptrs[] = {e->blob, e->Lh, e->sel, e->forced, e->yPrev, e->yCur, e->yOut, e->ring, e->xtOut, e->skipOut,
+                    e->Zs, e->Za, e->P, e->stage_dev, e->tc_image};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete e;
+    return 0;
+}
+
+int nvwn_set_embeddings(nvwn_engine* e, const float* embedPrev, const float* embedCur)
+{
+    if (!e || !embedPrev || !embedCur) return fail(NVWN_EINVAL, "nvwn_set_embeddings: NULL argument");
+    int rc;
+    if ((rc = upload(e, e->blob + e->o_embPrev, embedPrev, (size_t)e->A * e->R))) return rc;
+    if ((rc = upload(e, e->blob + e->o_embCur, embedCur, (size_t)e->A * e->R))) return rc;
+    e->tc_dirty = true;
+    CK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int nvwn_set_layer_weights(nvwn_engine* e, int layer, const float* Wprev, const float* Wcur, const float* Bh,
+                           const float* Wres, const float* Bres, const float* Wskip, const float* Bskip)
+{
+    if (!e || !Wprev || !Wcur || !Bh || !Wres || !Bres || !Wskip || !Bskip) return fail(NVWN_EINVAL, "nvwn_set_layer_weights: NULL argument");
+    if (layer < 0 || layer >= e->L) return fail(NVWN_EINVAL, "nvwn_set_layer_weights: layer out of range");
+    const size_t R = e->R, S = e->S, l = layer, td = e->td;
+    int rc;
+    if ((rc = upload(e, e->blob + e->o_Wprev + l * 2 * R * R * td, Wprev, 2 * R * R))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Wcur + l * 2 * R * R * td, Wcur, 2 * R * R))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Bh + l * 2 * R * td, Bh, 2 * R))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Wres + l * R * R * td, Wres, R * R))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Bres + l * R * td, Bres, R))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Wskip + l * S * R * td, Wskip, S * R))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Bskip + l * S * td, Bskip, S))) return rc;
+    e->tc_dirty = true;
+    CK(cudaStreamSynchronize(0));       // sources may be freed by the caller right after return
+    return 0;
+}
+
+int nvwn_set_out_weights(nvwn_engine* e, const float* Wzs, const float* Bzs, const float* Wza, const float* Bza)
+{
+    if (!e || !Wzs || !Bzs || !Wza || !Bza) return fail(NVWN_EINVAL, "nvwn_set_out_weights: NULL argument");
+    const size_t A = e->A, S = e->S;
+    int rc;
+    if ((rc = upload(e, e->blob + e->o_Wzs, Wzs, A * S))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Bzs, Bzs, A))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Wza, Wza, A * A))) return rc;
+    if ((rc = upload(e, e->blob + e->o_Bza, Bza, A))) return rc;
+    e->tc_dirty = true;
+    CK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int nvwn_reset_history(nvwn_engine* e)
+{
+    if (!e) return fail(NVWN_EINVAL, "nvwn_reset_history: NULL engine");
+    CK(wn_fill_int(e->yPrev, 128, e->B, 0));      // silenceInputs, nv_wavenet.cuh:213-218
+    CK(wn_fill_int(e->yCur, 128, e->B, 0));
+    return 0;
+}
+
+int nvwn_set_selectors(nvwn_engine* e, const float* selectors)
+{
+    if (!e || !selectors) return fail(NVWN_EINVAL, "nvwn_set_selectors: NULL argument");
+    CK(cudaMemcpy(e->sel, selectors, (size_t)e->N * e->B * sizeof(float), cudaMemcpyDefault));
+    return 0;
+}
+
+int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int num_samples, void* stream)
+{
+    if (!e || !Lh) return fail(NVWN_EINVAL, "nvwn_set_conditioning: NULL argument");
+    if (first_sample < 0 || num_samples < 0 || first_sample + num_samples > e->N) return fail(NVWN_EINVAL, "nvwn_set_conditioning: sample range out of bounds");
+    const size_t per = (size_t)e->L * e->B * 2 * e->R;
+    return upload(e, static_cast<char*>(e->Lh) + (size_t)first_sample * per * e->td, Lh, per * num_samples, (cudaStream_t)stream);
+}
+
+int nvwn_set_inputs(nvwn_engine* e, const float* Lh, const float* selectors)
+{
+    if (!e || !Lh || !selectors) return fail(NVWN_EINVAL, "nvwn_set_inputs: NULL argument");
+    int rc;
+    if ((rc = nvwn_reset_history(e))) return rc;
+    if ((rc = nvwn_set_conditioning(e, Lh, 0, e->N, nullptr))) return rc;
+    if ((rc = nvwn_set_selectors(e, selectors))) return rc;
+    CK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int nvwn_set_forced(nvwn_engine* e, const int* forced)
+{
+    if (!e) return fail(NVWN_EINVAL, "nvwn_set_forced: NULL engine");
+    if (!forced) { e->use_forced = false; return 0; }
+    CK(cudaMemcpy(e->forced, forced, (size_t)e->N * e->B * sizeof(int), cudaMemcpyDefault));
+    e->use_forced = true;
+    return 0;
+}
+
+int nvwn_weight_blob(nvwn_engine* e, void** dev_ptr, unsigned long long* bytes)
+{
+    if (!e || !dev_ptr || !bytes) return fail(NVWN_EINVAL, "nvwn_weight_blob: NULL argument");
+    *dev_ptr = e->blob;
+    *bytes = e->blob_bytes;
+    return 0;
+}
+
+int nvwn_weights_updated(nvwn_engine* e)
+{
+    if (!e) return fail(NVWN_EINVAL, "nvwn_weights_updated: NULL engine");
+    e->tc_dirty = true;
+    return 0;
+}
+
+int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples, int batch_size,
+                     int* yOut, int dump_activations, void* stream_)
+{
+    if (!e) return fail(NVWN_EINVAL, "nvwn_run_partial: NULL engine");
+    if (batch_size < 1 || batch_size > e->B || num_samples < 1 || num_samples > e->N)
+        return fail(NVWN_EINVAL, "nvwn_run_partial: batch_size / num_samples exceed what the engine was created for");
+    if (init_sample < 0 || count < 0 || init_sample + count > num_samples) return fail(NVWN_EINVAL, "nvwn_run_partial: sample range out of bounds");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    WnParams p;
+    fill_params(e, p, init_sample, count, num_samples, batch_size, dump_activations ? 1 : 0);
+    if (count > 0) {
+        if (want_tc(e, batch_size)) {
+            if (e->tc_dirty) {
+                CK(wn_tc_pack(e->tc_image, p, stream));
+                e->tc_dirty = false;
+            }
+            CK(wn_launch_tc(p, e->tc_image, stream, &e->last));
+        } else {
+            CK(wn_launch_stream(p, e->dtype == NVWN_FP16, stream, &e->last));
+        }
+        e->launches++;
+    }
+    if (yOut) CK(cudaMemcpyAsync(yOut, e->yOut, (size_t)num_samples * batch_size * sizeof(int), cudaMemcpyDefault, stream));
+    return 0;
+}
+
+int nvwn_run(nvwn_engine* e, int num_samples, int batch_size, int* yOut, int dump_activations, void* stream)
+{
+    return nvwn_run_partial(e, 0, num_samples, num_samples, batch_size, yOut, dump_activations, stream);
+}
+
+int nvwn_get_yout(nvwn_engine* e, int* yOut, int offset, int size, void* stream)
+{
+    if (!e || !yOut) return fail(NVWN_EINVAL, "nvwn_get_yout: NULL argument");
+    if (offset < 0 || size < 0 || offset + size > e->N) return fail(NVWN_EINVAL, "nvwn_get_yout: range out of bounds");
+    if (size == 0) return 0;
+    const size_t pitch = (size_t)e->N * sizeof(int);
+    CK(cudaMemcpy2DAsync(yOut + offset, pitch, e->yOut + offset, pitch, (size_t)size * sizeof(int), e->B, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+
+int nvwn_get_xt_out(nvwn_engine* e, int layer, float* out)
+{
+    if (!e || !out || layer < 0 || layer >= e->L) return fail(NVWN_EINVAL, "nvwn_get_xt_out: bad argument");
+    return download(out, e->xtOut + (size_t)layer * e->B * e->R, (size_t)e->B * e->R);
+}
+int nvwn_get_skip_out(nvwn_engine* e, int layer, float* out)
+{
+    if (!e || !out || layer < 0 || layer >= e->L) return fail(NVWN_EINVAL, "nvwn_get_skip_out: bad argument");
+    return download(out, e->skipOut + (size_t)layer * e->B * e->S, (size_t)e->B * e->S);
+}
+int nvwn_get_zs(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_zs: NULL") : download(out, e->Zs, (size_t)e->B * e->A); }
+int nvwn_get_za(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_za: NULL") : download(out, e->Za, (size_t)e->B * e->A); }
+int nvwn_get_p(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_p: NULL") : download(out, e->P, (size_t)e->B * e->A); }
+
+int nvwn_get_launch_info(nvwn_engine* e, nvwn_launch_info* info)
+{
+    if (!e || !info) return fail(NVWN_EINVAL, "nvwn_get_launch_info: NULL argument");
+    info->kernel = e->last.kernel; info->grid = e->last.grid; info->block = e->last.block;
+    info->smem_bytes = e->last.smem_bytes; info->batch_per_cta = e->last.batch_per_cta; info->cluster = e->last.cluster;
+    info->launches = e->launches;
+    const unsigned long long R = e->R, S = e->S, A = e->A, L = e->L;
+    info->weight_bytes = e->td * (L * (2 * 2 * R * R + R * R + S * R + 3 * R + S) + A * S + A * A + 2 * A);
+    return 0;
+}
+
+}  // extern "C"

@@ -39,21 +39,24 @@ static double wno_exp_core(double x)
     double kd = rint(x * LOG2E);
     double r = fma(-kd, LN2_HI, x);
     r = fma(-kd, LN2_LO, r);
-    /* Taylor series of exp(r), |r| <= ln2/2, degree 13, Horner */
-    double p = 0x1.6124613a86d09p-33;        /* 1/13! */
-    p = fma(p, r, 0x1.1eed8eff8d898p-29);    /* 1/12! */
-    p = fma(p, r, 0x1.ae64567f544e4p-26);    /* 1/11! */
-    p = fma(p, r, 0x1.27e4fb7789f5cp-22);    /* 1/10! */
-    p = fma(p, r, 0x1.71de3a556c734p-19);    /* 1/9!  */
-    p = fma(p, r, 0x1.a01a01a01a01ap-16);    /* 1/8!  */
-    p = fma(p, r, 0x1.a01a01a01a01ap-13);    /* 1/7!  */
-    p = fma(p, r, 0x1.6c16c16c16c17p-10);    /* 1/6!  */
-    p = fma(p, r, 0x1.1111111111111p-7);     /* 1/5!  */
-    p = fma(p, r, 0x1.5555555555555p-5);     /* 1/4!  */
-    p = fma(p, r, 0x1.5555555555555p-3);     /* 1/3!  */
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    /* degree-13 Taylor polynomial of exp(r), |r| <= ln2/2, Estrin association (fixed: the CUDA
+     * kernel evaluates exactly this tree) */
+    double a0 = fma(1.0, r, 1.0);                                           /* c0 + c1 r   */
+    double a1 = fma(0x1.5555555555555p-3, r, 0.5);                           /* c2 + c3 r   */
+    double a2 = fma(0x1.1111111111111p-7, r, 0x1.5555555555555p-5);          /* c4 + c5 r   */
+    double a3 = fma(0x1.a01a01a01a01ap-13, r, 0x1.6c16c16c16c17p-10);        /* c6 + c7 r   */
+    double a4 = fma(0x1.71de3a556c734p-19, r, 0x1.a01a01a01a01ap-16);        /* c8 + c9 r   */
+    double a5 = fma(0x1.ae64567f544e4p-26, r, 0x1.27e4fb7789f5cp-22);        /* c10 + c11 r */
+    double a6 = fma(0x1.6124613a86d09p-33, r, 0x1.1eed8eff8d898p-29);        /* c12 + c13 r */
+    double r2 = r * r;
+    double b0 = fma(a1, r2, a0);
+    double b1 = fma(a3, r2, a2);
+    double b2 = fma(a5, r2, a4);
+    double r4 = r2 * r2;
+    double d0 = fma(b1, r4, b0);
+    double d1 = fma(a6, r4, b2);
+    double r8 = r4 * r4;
+    double p = fma(d1, r8, d0);
     int64_t k = (int64_t)kd;                 /* -217 .. 145: 2^k is a normal double */
     uint64_t bits = (uint64_t)(k + 1023) << 52;
     double scale;

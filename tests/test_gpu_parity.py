@@ -1,0 +1,209 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle.
+
+fp32: bit-exact (indices AND every dumped activation) against oracle PORTABLE mode, which
+test_oracle_pin.py pins to the reference CPU model; and exact indices against the golden vectors of
+the reference's own nvWavenetReference on its 16 test runs (nv_wavenet_test.cu:343-394).
+fp16: logits within 1e-2 relative (BASELINE.json north_star) at matched history (teacher forcing).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import nv_wavenet_b200 as nw
+from oracle import pyoracle as po
+from tests import common, refgen
+
+pytestmark = pytest.mark.gpu
+
+RUNS = common.reference_runs()
+
+
+def gpu_engine(w, L, B, N, R, S, A, md, dtype=nw.FP32, tanh_embed=True, impl=nw.AUTO):
+    e = nw.NVWavenetInfer(L, md, B, N, impl, tanh_embed, R=R, S=S, A=A, dtype=dtype)
+    e.load(w)
+    e.set_inputs(w["Lh"], w["selectors"])
+    return e
+
+
+def cpu_oracle(w, L, B, N, R, S, A, md, math=po.MATH_PORTABLE, prec=po.PREC_FP32, tanh_embed=True):
+    o = po.Oracle(L, B, N, R, S, A, md, math=math, prec=prec, tanh_embed=tanh_embed)
+    o.load(w)
+    o.set_inputs(w["Lh"], w["selectors"])
+    return o
+
+
+def assert_acts_bit_equal(ao, ag):
+    for k in ("xt", "skip", "zs", "za", "p"):
+        assert common.bits_equal(ao[k], ag[k]), f"{k}: max abs diff {np.abs(ao[k] - ag[k]).max()}"
+
+
+@pytest.mark.parametrize("run", RUNS, ids=[r[0] for r in RUNS])
+def test_fp32_reference_test_runs(run):
+    """The reference's own integration test, replayed: run_chunks(7, ...) twice, exact yOut, activations."""
+    key, seed, i, R, S, A, L = run
+    B, N, md = common.B_REF, common.N_REF, common.MAXDIL_REF
+    w = common.reference_inputs(seed, i)
+    g = common.golden()
+    e = gpu_engine(w, L, B, N, R, S, A, md)
+    o = cpu_oracle(w, L, B, N, R, S, A, md)
+    for it in range(common.ITERS_REF):
+        y = np.zeros((B, N), np.int32)
+        seen = []
+        assert e.run_chunks(7, lambda yo, init, n: seen.append((init, n)), N, B, y)
+        e.synchronize()
+        assert seen == [(0, 7), (7, 1)]
+        yo = o.run(N, B)
+        assert np.array_equal(y, g[key + "/y"][it]), "sampled indices differ from the reference CPU model"
+        assert np.array_equal(y, yo)
+        ag = e.activations()
+        assert_acts_bit_equal(o.activations(), ag)
+        # the reference test's own tolerances against its CPU model (nv_wavenet_test.cu:273-298)
+        assert common.matrix_compare_ok(g[key + "/za"][it], ag["za"], 1e-4)
+        assert common.matrix_compare_ok(g[key + "/p"][it], ag["p"], 1e-3)
+        assert common.matrix_compare_ok(g[key + "/xt_last"][it], ag["xt"][-1], 1e-2)
+        assert common.matrix_compare_ok(g[key + "/skip_last"][it], ag["skip"][-1], 1e-2, relu=True)
+
+
+@pytest.mark.parametrize("shape", [
+    # R, S, A, L, B, N, maxDil, BT
+    (32, 128, 256, 5, 4, 40, 4, 1),
+    (32, 128, 256, 5, 4, 40, 4, 4),
+    (64, 128, 256, 4, 6, 24, 8, 2),
+    (64, 256, 256, 6, 8, 70, 16, 4),      # ring wraps (N > maxDil+1) and dilation cycle restarts
+    (64, 256, 256, 3, 3, 9, 2, 1),
+    (128, 256, 256, 3, 4, 12, 4, 2),
+    (64, 128, 512, 2, 2, 10, 2, 1),
+    (128, 256, 1024, 2, 2, 6, 2, 2),
+])
+@pytest.mark.parametrize("gen", ["lively", "uniform"])
+def test_fp32_bit_exact_fresh_shapes(shape, gen, monkeypatch):
+    R, S, A, L, B, N, md, bt = shape
+    monkeypatch.setenv("NVWN_STREAM_BT", str(bt))
+    w = (refgen.lively_inputs if gen == "lively" else refgen.synthetic_inputs)(99 + R + N, R, S, A, L, B, N)
+    e = gpu_engine(w, L, B, N, R, S, A, md)
+    o = cpu_oracle(w, L, B, N, R, S, A, md)
+    y = np.zeros((B, N), np.int32)
+    assert e.run(N, B, y, dump_activations=True)
+    e.synchronize()
+    assert e.launch_info()["batch_per_cta"] == bt
+    assert np.array_equal(y, o.run(N, B))
+    assert_acts_bit_equal(o.activations(), e.activations())
+    if gen == "lively":
+        assert len(np.unique(y)) > 8          # a non-degenerate sampled distribution
+
+
+def test_fp32_no_tanh_embed_and_forced_history():
+    """tanhEmbed=false (the PyTorch export path, pytorch/wavenet.py:153-154) and teacher forcing."""
+    R, S, A, L, B, N, md = 64, 256, 256, 4, 4, 20, 8
+    w = refgen.lively_inputs(5, R, S, A, L, B, N)
+    forced = np.random.default_rng(1).integers(0, A, (B, N)).astype(np.int32)
+    e = gpu_engine(w, L, B, N, R, S, A, md, tanh_embed=False)
+    o = cpu_oracle(w, L, B, N, R, S, A, md, tanh_embed=False)
+    e.set_forced(forced); o.set_forced(forced)
+    y = np.zeros((B, N), np.int32)
+    e.run(N, B, y, dump_activations=True); e.synchronize()
+    assert np.array_equal(y, o.run(N, B))
+    assert_acts_bit_equal(o.activations(), e.activations())
+
+
+def test_fp32_properties_at_full_model_size():
+    """C3-sized model (L20 R64 S256 A256, maxDil 512), longer than the oracle can follow cheaply:
+    chunked == unchunked, batch shards == whole batch, run-to-run determinism."""
+    R, S, A, L, B, N, md = 64, 256, 256, 20, 8, 600, 512
+    w = refgen.lively_inputs(11, R, S, A, L, B, N)
+    e = gpu_engine(w, L, B, N, R, S, A, md)
+    y1 = np.zeros((B, N), np.int32); e.run(N, B, y1); e.synchronize()
+    # determinism
+    e.reset_history(); y2 = np.zeros((B, N), np.int32); e.run(N, B, y2); e.synchronize()
+    assert np.array_equal(y1, y2)
+    # chunked
+    e.reset_history(); y3 = np.zeros((B, N), np.int32)
+    e.run_chunks(97, lambda *a: None, N, B, y3); e.synchronize()
+    assert np.array_equal(y1, y3)
+    # batch shards: utterances never interact
+    for lo, hi in ((0, 4), (4, 8)):
+        ws = dict(w); ws["Lh"] = np.ascontiguousarray(w["Lh"][:, :, lo:hi]); ws["selectors"] = np.ascontiguousarray(w["selectors"][:, lo:hi])
+        es = gpu_engine(ws, L, hi - lo, N, R, S, A, md)
+        ys = np.zeros((hi - lo, N), np.int32); es.run(N, hi - lo, ys); es.synchronize()
+        assert np.array_equal(ys, y1[lo:hi])
+    # oracle agrees on a prefix it can afford
+    n0 = 48
+    w0 = dict(w); w0["Lh"] = np.ascontiguousarray(w["Lh"][:n0]); w0["selectors"] = np.ascontiguousarray(w["selectors"][:n0])
+    o = cpu_oracle(w0, L, B, n0, R, S, A, md)
+    assert np.array_equal(o.run(n0, B), y1[:, :n0])
+
+
+def test_fp32_device_pointers():
+    """Weights / inputs / yOut given as device pointers (nv_wavenet_test.cu:133-239 variants)."""
+    import torch
+    R, S, A, L, B, N, md = 64, 128, 256, 3, 4, 10, 4
+    w = refgen.lively_inputs(3, R, S, A, L, B, N)
+    wd = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+    e = nw.NVWavenetInfer(L, md, B, N, R=R, S=S, A=A)
+    e.load(wd); e.set_inputs(wd["Lh"], wd["selectors"])
+    yd = torch.zeros((B, N), dtype=torch.int32, device="cuda")
+    e.run(N, B, yd, dump_activations=True); e.synchronize()
+    o = cpu_oracle(w, L, B, N, R, S, A, md)
+    assert np.array_equal(yd.cpu().numpy(), o.run(N, B))
+
+
+def _logit_check(za_o, za_g, rel=1e-2):
+    """1e-2 relative on logits; logits that cancel to ~0 are judged against the row's scale."""
+    scale = np.abs(za_o).max(axis=-1, keepdims=True)
+    assert np.all(np.abs(za_g - za_o) <= rel * np.maximum(np.abs(za_o), 0.05 * scale)), \
+        f"max rel-to-scale err {(np.abs(za_g - za_o) / scale).max()}"
+
+
+@pytest.mark.parametrize("kernel", ["stream", "auto"])
+@pytest.mark.parametrize("shape", [
+    (64, 256, 256, 20, 8, 24, 8),
+    (64, 128, 256, 20, 4, 16, 4),
+    (64, 256, 256, 20, 64, 12, 4),
+])
+def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
+    R, S, A, L, B, N, md = shape
+    if kernel == "stream":
+        monkeypatch.setenv("NVWN_FP16_KERNEL", "stream")
+    w = refgen.lively_inputs(21 + B, R, S, A, L, B, N)
+    # moderate the scales a little so that fp16 GEMM inputs stay well inside range
+    o32 = cpu_oracle(w, L, B, N, R, S, A, md)
+    forced = o32.run(N, B)                                     # the fp32 model's own trajectory as history
+    for n_run in (1, N):                                       # step 0 (identical history) and the last step
+        wn_ = dict(w); wn_["Lh"] = np.ascontiguousarray(w["Lh"][:n_run]); wn_["selectors"] = np.ascontiguousarray(w["selectors"][:n_run])
+        f = np.ascontiguousarray(forced[:, :n_run])
+        e = gpu_engine(wn_, L, B, n_run, R, S, A, md, dtype=nw.FP16)
+        e.set_forced(f)
+        y = np.zeros((B, n_run), np.int32)
+        e.run(n_run, B, y, dump_activations=True); e.synchronize()
+        o16 = cpu_oracle(wn_, L, B, n_run, R, S, A, md, prec=po.PREC_FP16); o16.set_forced(f); o16.run(n_run, B)
+        o = cpu_oracle(wn_, L, B, n_run, R, S, A, md); o.set_forced(f); o.run(n_run, B)
+        ag = e.activations()
+        _logit_check(o16.get_za(), ag["za"], 2e-3)             # vs the fp16-contract oracle: tight
+        _logit_check(o.get_za(), ag["za"], 1e-2)               # vs fp32 oracle: the north-star tolerance
+        assert np.allclose(ag["p"].sum(axis=1), 1.0, atol=1e-3)
+        assert np.abs(ag["p"] - o.get_p()).max() <= 1e-2 * o.get_p().max()
+
+
+def test_wavenet_infer_c_abi_drop_in():
+    """The reference C-ABI entry point (pytorch/wavenet_infer.h:28-58): float** layer arrays, selectors
+    from libc rand() -- seeded here so the expected draw can be replayed -- zero output biases."""
+    from nv_wavenet_b200 import _lib
+    lib = _lib.lib()
+    R, S, A = lib.get_R(), lib.get_S(), lib.get_A()
+    L, B, N, md = 4, 4, 16, 4
+    w = refgen.lively_inputs(77, R, S, A, L, B, N)
+    libc = C.CDLL(None)
+    libc.srand(1234)
+    arr = lambda key: (C.c_void_p * L)(*[w[key][l].ctypes.data for l in range(L)])
+    samples = np.zeros((B, N), np.int32)
+    lib.wavenet_infer(N, B, w["embPrev"].ctypes.data, w["embCur"].ctypes.data, L, md,
+                      arr("Wprev"), arr("Wcur"), arr("Bh"), arr("Wres"), arr("Bres"), arr("Wskip"), arr("Bskip"),
+                      w["Wzs"].ctypes.data, w["Wza"].ctypes.data, 1, w["Lh"].ctypes.data, 3, samples.ctypes.data)
+    # expected selectors: Matrix(batch, samples).randomize(0.5, 1.0) on the same rand() stream
+    rng = refgen.GlibcRand(1234)
+    sel = refgen.randomize(rng, B, N, np.float32(0.5), np.float32(1.0)).reshape(N, B)
+    w2 = dict(w); w2["selectors"] = sel; w2["Bzs"] = np.zeros(A, np.float32); w2["Bza"] = np.zeros(A, np.float32)
+    o = cpu_oracle(w2, L, B, N, R, S, A, md)
+    assert np.array_equal(samples, o.run(N, B))
