@@ -49,7 +49,9 @@ template <> struct Num<__half> {
 };
 
 // acc[b] = sum_k W[row + k*M] * xs[b][k], k ascending (matrix.cpp:85-102 order).
-template <typename TD, int BT>
+// KB weights are requested back to back before the first use, so the L2 latency is paid once per
+// KB columns instead of once per 8.
+template <typename TD, int BT, int KB>
 __device__ __forceinline__ void dot_cols(const TD* __restrict__ W, int M, int K, int row,
                                          const float* __restrict__ xs, float (&acc)[BT])
 {
@@ -57,29 +59,22 @@ __device__ __forceinline__ void dot_cols(const TD* __restrict__ W, int M, int K,
 #pragma unroll
     for (int b = 0; b < BT; b++) acc[b] = 0.f;
     const TD* wp = W + row;
-#pragma unroll 2
-    for (int k0 = 0; k0 < K; k0 += 8) {
-        float w[8];
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += KB) {
+        float w[KB];
 #pragma unroll
-        for (int j = 0; j < 8; j++) w[j] = N::ld(wp + (size_t)(k0 + j) * M);
+        for (int j = 0; j < KB; j++) w[j] = N::ld(wp + (size_t)(k0 + j) * M);
 #pragma unroll
-        for (int b = 0; b < BT; b++) {
-            const float4 xa = *reinterpret_cast<const float4*>(xs + b * K + k0);
-            const float4 xb = *reinterpret_cast<const float4*>(xs + b * K + k0 + 4);
-            float a = acc[b];
-            a = N::mac(a, w[0], xa.x); a = N::mac(a, w[1], xa.y); a = N::mac(a, w[2], xa.z); a = N::mac(a, w[3], xa.w);
-            a = N::mac(a, w[4], xb.x); a = N::mac(a, w[5], xb.y); a = N::mac(a, w[6], xb.z); a = N::mac(a, w[7], xb.w);
-            acc[b] = a;
+        for (int j = 0; j < KB; j += 4) {
+#pragma unroll
+            for (int b = 0; b < BT; b++) {
+                const float4 xa = *reinterpret_cast<const float4*>(xs + b * K + k0 + j);
+                float a = acc[b];
+                a = N::mac(a, w[j], xa.x); a = N::mac(a, w[j + 1], xa.y); a = N::mac(a, w[j + 2], xa.z); a = N::mac(a, w[j + 3], xa.w);
+                acc[b] = a;
+            }
         }
     }
-}
-
-// Pull the first `n` weight columns of `row` towards L1 ahead of the barrier that precedes their use.
-template <typename TD>
-__device__ __forceinline__ void prefetch_cols(const TD* W, int M, int row, int n)
-{
-    const TD* wp = W + row;
-    for (int k = 0; k < n; k++) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (size_t)k * M));
 }
 
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
@@ -101,6 +96,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
     constexpr int NT = Shape<R, S>::NT;
     constexpr int NACT = 2 * R * BT;
     constexpr int ACT_PER = (NACT + NT - 1) / NT;
+    constexpr int KBR = R < 64 ? R : 64;          // weight columns in flight per thread in the R-deep dots
     static_assert(R * BT <= NT, "one x-task per thread");
 
     const int tid = threadIdx.x;
@@ -212,16 +208,12 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
             }
 
             // ---- stage 1: a_prev = Wprev.x[t-d], a_cur = Wcur.x[t]  (reference.cpp:61-65) ----
-            if (tid < R + S) {      // warm L1 with the head of this thread's stage-3 weight row
-                if (tid < R) prefetch_cols(Wres + (size_t)l * R * R, R, tid, 16);
-                else prefetch_cols(Wskip + (size_t)l * S * R, S, tid - R, 16);
-            }
             if (tid < 4 * R) {
                 const bool cur = tid >= 2 * R;
                 const int row = cur ? tid - 2 * R : tid;
                 const TD* W = (cur ? Wcur : Wprev) + (size_t)l * 2 * R * R;
                 float acc[BT];
-                dot_cols<TD, BT>(W, 2 * R, R, row, cur ? xq : xp, acc);
+                dot_cols<TD, BT, KBR>(W, 2 * R, R, row, cur ? xq : xp, acc);
                 float* dst = cur ? ac : ap;
 #pragma unroll
                 for (int b = 0; b < BT; b++) dst[b * 2 * R + row] = acc[b];
@@ -251,18 +243,13 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
             __syncthreads();
 
             // ---- stage 3: residual (reference.cpp:82-84) and skip (reference.cpp:86-90) ----
-            if (l + 1 < L) {
-                if (tid < 4 * R) prefetch_cols((tid >= 2 * R ? Wcur : Wprev) + (size_t)(l + 1) * 2 * R * R, 2 * R, tid % (2 * R), 16);
-            } else if (tid < A) {
-                prefetch_cols(Wzs, A, tid, 16);
-            }
             if (tid < R + S) {
                 const bool is_res = tid < R;
                 const int row = is_res ? tid : tid - R;
                 const TD* W = is_res ? Wres + (size_t)l * R * R : Wskip + (size_t)l * S * R;
                 const float bias = is_res ? N::ld(Bres + (size_t)l * R + row) : N::ld(Bskip + (size_t)l * S + row);
                 float acc[BT];
-                dot_cols<TD, BT>(W, is_res ? R : S, R, row, hq, acc);
+                dot_cols<TD, BT, KBR>(W, is_res ? R : S, R, row, hq, acc);
                 if (is_res) {
 #pragma unroll
                     for (int b = 0; b < BT; b++) {
@@ -288,11 +275,10 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
         }
 
         // ---- output layers (reference.cpp:93-104) ----
-        if (tid < A) prefetch_cols(Wza, A, tid, 16);
         for (int row = tid; row < A; row += NT) {
             float acc[BT];
             const float bias = N::ld(Bzs + row);
-            dot_cols<TD, BT>(Wzs, A, S, row, skq, acc);
+            dot_cols<TD, BT, 32>(Wzs, A, S, row, skq, acc);
 #pragma unroll
             for (int b = 0; b < BT; b++) {
                 float v = N::add(acc[b], bias);
@@ -302,11 +288,10 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
             }
         }
         __syncthreads();
-        if (tid < 4 * R) prefetch_cols(tid >= 2 * R ? Wcur : Wprev, 2 * R, tid % (2 * R), 16);
         for (int row = tid; row < A; row += NT) {
             float acc[BT];
             const float bias = N::ld(Bza + row);
-            dot_cols<TD, BT>(Wza, A, A, row, zsq, acc);
+            dot_cols<TD, BT, 32>(Wza, A, A, row, zsq, acc);
 #pragma unroll
             for (int b = 0; b < BT; b++) {
                 const float v = N::add(acc[b], bias);
