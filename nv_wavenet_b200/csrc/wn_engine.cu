@@ -19,6 +19,7 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image, cudaStream_t s
 bool wn_tc_supported(int R, int S, int A, int L, int B);
 size_t wn_tc_image_bytes(int R, int S, int A, int L);
 cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream);
+size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B);
 
 namespace {
 
@@ -202,7 +203,12 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     ALLOC(e->yPrev, Bz * sizeof(int));
     ALLOC(e->yCur, Bz * sizeof(int));
     ALLOC(e->yOut, Nz * Bz * sizeof(int));
-    ALLOC(e->ring, (size_t)(max_dilation + 1) * L * Bz * R * td);
+    size_t ring_bytes = (size_t)(max_dilation + 1) * L * Bz * R * td;
+    if (dtype == NVWN_FP16 && wn_tc_supported(R, S, A, num_layers, batch_size)) {
+        const size_t tcb = wn_tc_ring_bytes(S, num_layers, max_dilation, batch_size);     // tiled history layout of the tensor-core kernel
+        if (tcb > ring_bytes) ring_bytes = tcb;
+    }
+    ALLOC(e->ring, ring_bytes);
     ALLOC(e->xtOut, L * Bz * R * sizeof(float));
     ALLOC(e->skipOut, L * Bz * S * sizeof(float));
     ALLOC(e->Zs, Bz * A * sizeof(float));
@@ -213,7 +219,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
 #undef ALLOC
     cudaMemsetAsync(e->blob, 0, e->blob_bytes, 0);
     cudaMemsetAsync(e->yOut, 0, Nz * Bz * sizeof(int), 0);
-    cudaMemsetAsync(e->ring, 0, (size_t)(max_dilation + 1) * L * Bz * R * td, 0);
+    cudaMemsetAsync(e->ring, 0, ring_bytes, 0);
     wn_fill_int(e->yPrev, 128, Bz, 0);
     wn_fill_int(e->yCur, 128, Bz, 0);
     cudaError_t se = cudaDeviceSynchronize();
