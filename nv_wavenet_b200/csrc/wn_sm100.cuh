@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace sm100 {
 
@@ -38,9 +39,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Bounded spin: a protocol slip must surface as a launch failure with a message, never as a hung GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity)
+{
+    printf("wn_tc: mbarrier wait timed out: block %d thread %d barrier@0x%x parity %u\n", blockIdx.x, threadIdx.x, bar_addr, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-    while (!mbar_try_wait(bar, parity)) {}
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) mbar_timeout(smem_u32(bar), parity);
+    }
 }
 
 // ------------------------------------------------------------------ fences

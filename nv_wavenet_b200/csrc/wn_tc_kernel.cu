@@ -515,30 +515,29 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 }
                 if (!found) base = run - csum[A / 16 - 1];
             }
+            // third pass: every lane walks all chunks (tcgen05.ld is warp-collective: uniform address, no divergence
+            // around it) and scans only inside its own chunk `cb`; the dump of Za / P rides along
             int y = A - 1;
             {
-                uint32_t v[16];
-                tmem_ld16(DZA + lane_off + 16 * cb, v);
-                tmem_ld_wait();
-                float run = base;
-                bool found = false;
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    run += wn::exp2f_fast((__uint_as_float(v[j]) + s_bza[16 * cb + j] - mx) * 1.4426950408889634f);
-                    if (!found && target < run) { y = 16 * cb + j; found = true; }
-                }
-                if (!found) y = (cb == A / 16 - 1) ? A - 1 : 16 * cb + 15;
-            }
-            if (dump && valid) {
                 const float inv = 1.f / total;
-                for (int c0 = 0; c0 < A; c0 += 16) {
+                bool found = false;
+#pragma unroll 1
+                for (int c = 0; c < A / 16; c++) {
                     uint32_t v[16];
-                    tmem_ld16(DZA + lane_off + c0, v);
+                    tmem_ld16(DZA + lane_off + 16 * c, v);
                     tmem_ld_wait();
-                    for (int j = 0; j < 16; j++) {
-                        const float z = __uint_as_float(v[j]) + s_bza[c0 + j];
-                        p.Za[(size_t)b * A + c0 + j] = z;
-                        p.P[(size_t)b * A + c0 + j] = wn::exp2f_fast((z - mx) * 1.4426950408889634f) * inv;
+                    if (c == cb || dump) {
+                        float run = base;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float z = __uint_as_float(v[j]) + s_bza[16 * c + j];
+                            const float e = wn::exp2f_fast((z - mx) * 1.4426950408889634f);
+                            if (c == cb) {
+                                run += e;
+                                if (!found && target < run) { y = 16 * c + j; found = true; }
+                            }
+                            if (dump && valid) { p.Za[(size_t)b * A + 16 * c + j] = z; p.P[(size_t)b * A + 16 * c + j] = e * inv; }
+                        }
                     }
                 }
             }
