@@ -40,7 +40,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     return ok != 0;
 }
 // Bounded spin: a protocol slip must surface as a launch failure with a message, never as a hung GPU.
-__device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity)
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity)
 {
     printf("wn_tc: mbarrier wait timed out: block %d thread %d barrier@0x%x parity %u\n", blockIdx.x, threadIdx.x, bar_addr, parity);
     __trap();
