@@ -304,6 +304,19 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 lh[4 * i] = v.x; lh[4 * i + 1] = v.y; lh[4 * i + 2] = v.z; lh[4 * i + 3] = v.w;
             }
         };
+        // History ring (global, read back d samples later by TMA): written AFTER the barrier arrival that publishes the
+        // shared-memory tile, so that the proxy fence in front of that arrival never waits for global stores (or for the
+        // conditioning loads below).  The stores are fenced by the next stage's fence.proxy.async, long before any TMA
+        // read of them (>= one full sample later).
+        auto store_history = [&](unsigned char* grow) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) o[j] = pack_h2(x[8 * q + 2 * j], x[8 * q + 2 * j + 1]);
+                *reinterpret_cast<uint4*>(grow + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        };
         if (t_begin < t_end) load_lh(t_begin, 0);
 
         for (int t = t_begin; t < t_end; t++) {
@@ -313,7 +326,6 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             {
                 const uint4* ep = reinterpret_cast<const uint4*>(embPrev + (size_t)yp * R);
                 const uint4* ec = reinterpret_cast<const uint4*>(embCur + (size_t)yc * R);
-                unsigned char* grow = ring_tile(t, 0);
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
                     const uint4 a = __ldg(ep + q), c = __ldg(ec + q);
@@ -328,13 +340,12 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         x[8 * q + 2 * j] = e0; x[8 * q + 2 * j + 1] = e1;
                         o[j] = pack_h2(e0, e1);
                     }
-                    const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q)) = ov;
-                    *reinterpret_cast<uint4*>(grow + chunk_off(row, q)) = ov;
+                    *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
                 tc_fence_before_sync();
                 fence_proxy_async();
                 mbar_arrive(epi_done);                                  // x_0 ready
+                store_history(ring_tile(t, 0));                         // off the critical path (see store_history)
             }
 
             for (int l = 0; l < L; l++) {
@@ -366,22 +377,10 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 tc_fence_before_sync();
                 fence_proxy_async();
                 mbar_arrive(epi_done);                                  // h ready, D1 free
-                // conditioning of the next layer (next sample when wrapping): issue now, consumed a layer later
-                {
-                    const bool wrap = (l + 1 == L);
-                    const int tn = wrap ? t + 1 : t, ln = wrap ? 0 : l + 1;
-                    if (tn < t_end) {
-                        load_lh(tn, ln);
-                        const bool wrap2 = (ln + 1 == L);
-                        const int t2 = wrap2 ? tn + 1 : tn, l2 = wrap2 ? 0 : ln + 1;
-                        if (t2 < t_end) { prefetch_l2(lh_ptr(t2, l2)); prefetch_l2(reinterpret_cast<const char*>(lh_ptr(t2, l2)) + 128); }
-                    }
-                }
                 // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
                 mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
                 tc_fence_after_sync();
                 const float* br = s_bres + (size_t)l * 64;
-                unsigned char* grow = (l + 1 < L) ? ring_tile(t, l + 1) : nullptr;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     uint32_t v[16];
@@ -402,14 +401,25 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         const uint4 o0 = make_uint4(o[0], o[1], o[2], o[3]), o1 = make_uint4(o[4], o[5], o[6], o[7]);
                         *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 2 * q)) = o0;
                         *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 2 * q + 1)) = o1;
-                        *reinterpret_cast<uint4*>(grow + chunk_off(row, 2 * q)) = o0;
-                        *reinterpret_cast<uint4*>(grow + chunk_off(row, 2 * q + 1)) = o1;
                     }
                 }
                 if (l + 1 < L) {
                     tc_fence_before_sync();
                     fence_proxy_async();
                     mbar_arrive(epi_done);                              // x_{l+1} ready
+                    store_history(ring_tile(t, l + 1));
+                }
+                // conditioning of the next layer (next sample when wrapping): issued here, consumed after the next MMA;
+                // the rows of the layer after that are pulled into L2 now
+                {
+                    const bool wrap = (l + 1 == L);
+                    const int tn = wrap ? t + 1 : t, ln = wrap ? 0 : l + 1;
+                    if (tn < t_end) {
+                        load_lh(tn, ln);
+                        const bool wrap2 = (ln + 1 == L);
+                        const int t2 = wrap2 ? tn + 1 : tn, l2 = wrap2 ? 0 : ln + 1;
+                        if (t2 < t_end) { prefetch_l2(lh_ptr(t2, l2)); prefetch_l2(reinterpret_cast<const char*>(lh_ptr(t2, l2)) + 128); }
+                    }
                 }
                 // ---------------- per-layer skip dump (last sample of a dumping launch only)
                 if (dump && l + 1 < L) {
