@@ -28,6 +28,9 @@ struct WnParams {
     int* yOut;                                          // [B][N]
     // last-sample activation dumps (fp32)
     float *xtOut, *skipOut, *Zs, *Za, *P;               // [L][B][R], [L][B][S], [B][A] x3
+    // optional timeline trace of one sample (debug): 3 x 1024 (tag << 48 | clock) words, or NULL
+    unsigned long long* trace;
+    int trace_t;
 };
 
 struct WnLaunchInfo {

@@ -72,6 +72,9 @@ struct nvwn_engine {
     void* tc_image = nullptr;                // tensor-core kernel's pre-tiled weight image
     bool tc_dirty = true;
 
+    unsigned long long* trace = nullptr;     // debug timeline (nvwn_debug_trace)
+    int trace_t = -1;
+
     WnLaunchInfo last{};
     unsigned long long launches = 0;
 
@@ -133,6 +136,7 @@ void fill_params(const nvwn_engine* e, WnParams& p, int init_sample, int count, 
     p.Lh = e->Lh; p.sel = e->sel; p.forced = e->use_forced ? e->forced : nullptr;
     p.yPrev = e->yPrev; p.yCur = e->yCur; p.ring = e->ring; p.yOut = e->yOut;
     p.xtOut = e->xtOut; p.skipOut = e->skipOut; p.Zs = e->Zs; p.Za = e->Za; p.P = e->P;
+    p.trace = e->trace; p.trace_t = e->trace_t;
 }
 
 }  // namespace
@@ -232,7 +236,7 @@ int nvwn_destroy(nvwn_engine* e)
 {
     if (!e) return 0;
     void* ptrs[] = {e->blob, e->Lh, e->sel, e->forced, e->yPrev, e->yCur, e->yOut, e->ring, e->xtOut, e->skipOut,
-                    e->Zs, e->Za, e->P, e->stage_dev, e->tc_image};
+                    e->Zs, e->Za, e->P, e->stage_dev, e->tc_image, e->trace};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete e;
     return 0;
@@ -394,6 +398,20 @@ int nvwn_get_skip_out(nvwn_engine* e, int layer, float* out)
 int nvwn_get_zs(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_zs: NULL") : download(out, e->Zs, (size_t)e->B * e->A); }
 int nvwn_get_za(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_za: NULL") : download(out, e->Za, (size_t)e->B * e->A); }
 int nvwn_get_p(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_p: NULL") : download(out, e->P, (size_t)e->B * e->A); }
+
+// debug only (not part of the public ABI): record a clock64 timeline of sample `t` of block 0 into `out` (3 x 1024 words)
+int nvwn_debug_trace(nvwn_engine* e, int t, unsigned long long* out_host, int fetch)
+{
+    if (!e) return NVWN_EINVAL;
+    if (!fetch) {
+        if (!e->trace) CK(cudaMalloc((void**)&e->trace, 3 * 1024 * sizeof(unsigned long long)));
+        CK(cudaMemset(e->trace, 0, 3 * 1024 * sizeof(unsigned long long)));
+        e->trace_t = t;
+        return 0;
+    }
+    CK(cudaMemcpy(out_host, e->trace, 3 * 1024 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 int nvwn_get_launch_info(nvwn_engine* e, nvwn_launch_info* info)
 {

@@ -179,6 +179,11 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     for (int d = 1; d <= p.maxDil; d <<= 1) cyc++;
     auto dil = [&](int l) -> int { return 1 << (l % cyc); };
 
+    // debug timeline: role r (0 epilogue thread 0, 1 MMA issuer, 2 producer) appends (tag << 48 | clock) words
+    unsigned long long* trc = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+    int trn = 0;
+#define TRACE(role, tag) do { if (trc && t == p.trace_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
+
     if (warp == 4) {
         // =============================================================== TMA producer
         if (lane == 0) {
@@ -194,6 +199,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 for (int l = 0; l < L; l++) {
                     const unsigned char* lw = img + (size_t)l * im.layer_bytes;
                     const int d = dil(l);
+                    TRACE(2, 100 + l);
                     if (t >= d) { put(ring_tile(t - d, l), TILE); put(lw, TILE); }
                     put(lw + TILE, TILE);
                     put(lw + 2 * TILE, TILE / 2);
@@ -233,6 +239,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 const bool dump = p.dump && (t == t_end - 1);
                 for (int l = 0; l < L; l++) {
                     wait_epi();                                         // x_l tile ready (and, for l = 0, Dza consumed)
+                    TRACE(1, 20);
                     const bool has_prev = t >= dil(l);
                     if (l == 0 && has_prev) prev(0);
                     {   // D1 += Wcur . x[t]
@@ -241,14 +248,17 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         mma4(xc_a, ring_a + s * TILE, D1, idesc128, has_prev);
                         umma_commit(&w_empty[s]);
                         umma_commit(d1_full);
+                        TRACE(1, 21);
                     }
                     wait_epi();                                         // h tile ready, D1 consumed
+                    TRACE(1, 22);
                     {   // Dx = Wres . h
                         const int s = wait_stage();
                         tc_fence_after_sync();
                         mma4(h_a, ring_a + s * TILE, DX, idesc64, false);
                         umma_commit(&w_empty[s]);
                         umma_commit(dx_full);
+                        TRACE(1, 23);
                     }
                     for (int c = 0; c < S / 128; c++) {                 // Dskip (+)= Wskip . h   (accumulates over layers)
                         const int s = wait_stage();
@@ -258,6 +268,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     }
                     if (dump || l == L - 1) umma_commit(skip_full);
                     if (l + 1 < L && t >= dil(l + 1)) prev(l + 1);      // off the critical path
+                    TRACE(1, 24);
                 }
                 wait_epi();                                             // relu(skip) tile ready
                 for (int kt = 0; kt < S / 64; kt++)
@@ -345,6 +356,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 tc_fence_before_sync();
                 fence_proxy_async();
                 mbar_arrive(epi_done);                                  // x_0 ready
+                if (tid == 0) TRACE(0, 1);
                 store_history(ring_tile(t, 0));                         // off the critical path (see store_history)
             }
 
@@ -352,6 +364,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 // ---------------- gate: h = tanh(a[0:R]) * sigmoid(a[R:2R]),  a = D1 + Bh + Lh   (reference.cpp:67-80)
                 mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
                 tc_fence_after_sync();
+                if (tid == 0) TRACE(0, 2);
                 const float* bh = s_bh + (size_t)l * 128;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -374,12 +387,15 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     *reinterpret_cast<uint4*>(t_h + chunk_off(row, 2 * q)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                     *reinterpret_cast<uint4*>(t_h + chunk_off(row, 2 * q + 1)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
                 }
+                if (tid == 0) TRACE(0, 12);
                 tc_fence_before_sync();
                 fence_proxy_async();
                 mbar_arrive(epi_done);                                  // h ready, D1 free
+                if (tid == 0) TRACE(0, 3);
                 // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
                 mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
                 tc_fence_after_sync();
+                if (tid == 0) TRACE(0, 4);
                 const float* br = s_bres + (size_t)l * 64;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -407,6 +423,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     tc_fence_before_sync();
                     fence_proxy_async();
                     mbar_arrive(epi_done);                              // x_{l+1} ready
+                    if (tid == 0) TRACE(0, 5);
                     store_history(ring_tile(t, l + 1));
                 }
                 // conditioning of the next layer (next sample when wrapping): issued here, consumed after the next MMA;
@@ -440,6 +457,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             // ---------------- relu(skip) -> GEMM input of the first output layer   (reference.cpp:88-90)
             mbar_wait(skip_full, ph_skip); ph_skip ^= 1;
             tc_fence_after_sync();
+            if (tid == 0) TRACE(0, 6);
 #pragma unroll 1
             for (int c0 = 0; c0 < S; c0 += 16) {
                 uint32_t v[16];
@@ -461,6 +479,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             tc_fence_before_sync();
             fence_proxy_async();
             mbar_arrive(epi_done);                                      // relu(skip) tile ready
+            if (tid == 0) TRACE(0, 7);
 
             // ---------------- Zs = relu(Wzs . skip + Bzs)   (reference.cpp:96-98)
             mbar_wait(out_full, ph_out); ph_out ^= 1;
@@ -486,10 +505,12 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             tc_fence_before_sync();
             fence_proxy_async();
             mbar_arrive(epi_done);                                      // relu(Zs) tile ready
+            if (tid == 0) TRACE(0, 9);
 
             // ---------------- Za, softmax, categorical sample -- all inside this thread   (reference.cpp:100-121)
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
+            if (tid == 0) TRACE(0, 10);
             float mx = 0.f;                                             // matrix.cpp:171 starts the max at 0
 #pragma unroll 1
             for (int c0 = 0; c0 < A; c0 += 16) {
@@ -557,6 +578,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 yp = yc;
                 yc = fb;
             }
+            if (tid == 0) TRACE(0, 11);
             // Dza is consumed: the x_0-ready arrival of the next sample (or kernel end) releases it
         }
         if (valid) { p.yPrev[b] = yp; p.yCur[b] = yc; }
