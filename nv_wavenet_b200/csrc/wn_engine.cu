@@ -20,6 +20,8 @@ bool wn_tc_supported(int R, int S, int A, int L, int B);
 size_t wn_tc_image_bytes(int R, int S, int A, int L);
 cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream);
 size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B);
+size_t wn_tc_cond_bytes(int L, int B, int N);
+cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
 
 namespace {
 
@@ -71,6 +73,7 @@ struct nvwn_engine {
 
     void* tc_image = nullptr;                // tensor-core kernel's pre-tiled weight image
     bool tc_dirty = true;
+    bool tc_mode = false;                    // decided once at creation: conditioning + history use the tiled layouts
 
     unsigned long long* trace = nullptr;     // debug timeline (nvwn_debug_trace)
     int trace_t = -1;
@@ -113,14 +116,14 @@ int download(float* dst, const float* src, size_t n)
     return 0;
 }
 
-bool want_tc(const nvwn_engine* e, int batch)
+bool decide_tc(int dtype, int impl, int R, int S, int A, int L, int B)
 {
-    if (e->dtype != NVWN_FP16) return false;
-    if (e->impl == NVWN_KERNEL_STREAM) return false;
+    if (dtype != NVWN_FP16) return false;
+    if (impl == NVWN_KERNEL_STREAM) return false;
     if (const char* env = getenv("NVWN_FP16_KERNEL")) {
         if (!strcmp(env, "stream")) return false;
     }
-    return wn_tc_supported(e->R, e->S, e->A, e->L, batch);
+    return wn_tc_supported(R, S, A, L, B);
 }
 
 void fill_params(const nvwn_engine* e, WnParams& p, int init_sample, int count, int num_samples, int batch, int dump)
@@ -201,14 +204,15 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
         }                                                                                     \
     } while (0)
     ALLOC(e->blob, e->blob_bytes);
-    ALLOC(e->Lh, Nz * L * Bz * 2 * R * td);
+    e->tc_mode = decide_tc(dtype, impl, R, S, A, num_layers, batch_size);
+    ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(num_layers, batch_size, num_samples) : Nz * L * Bz * 2 * R * td);
     ALLOC(e->sel, Nz * Bz * sizeof(float));
     ALLOC(e->forced, Nz * Bz * sizeof(int));
     ALLOC(e->yPrev, Bz * sizeof(int));
     ALLOC(e->yCur, Bz * sizeof(int));
     ALLOC(e->yOut, Nz * Bz * sizeof(int));
     size_t ring_bytes = (size_t)(max_dilation + 1) * L * Bz * R * td;
-    if (dtype == NVWN_FP16 && wn_tc_supported(R, S, A, num_layers, batch_size)) {
+    if (e->tc_mode) {
         const size_t tcb = wn_tc_ring_bytes(S, num_layers, max_dilation, batch_size);     // tiled history layout of the tensor-core kernel
         if (tcb > ring_bytes) ring_bytes = tcb;
     }
@@ -219,7 +223,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     ALLOC(e->Za, Bz * A * sizeof(float));
     ALLOC(e->P, Bz * A * sizeof(float));
     if (e->stage_elems) ALLOC(e->stage_dev, e->stage_elems * sizeof(float));
-    if (dtype == NVWN_FP16 && wn_tc_supported(R, S, A, num_layers, batch_size)) ALLOC(e->tc_image, wn_tc_image_bytes(R, S, A, num_layers));
+    if (e->tc_mode) ALLOC(e->tc_image, wn_tc_image_bytes(R, S, A, num_layers));
 #undef ALLOC
     cudaMemsetAsync(e->blob, 0, e->blob_bytes, 0);
     cudaMemsetAsync(e->yOut, 0, Nz * Bz * sizeof(int), 0);
@@ -306,7 +310,23 @@ int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int
     if (!e || !Lh) return fail(NVWN_EINVAL, "nvwn_set_conditioning: NULL argument");
     if (first_sample < 0 || num_samples < 0 || first_sample + num_samples > e->N) return fail(NVWN_EINVAL, "nvwn_set_conditioning: sample range out of bounds");
     const size_t per = (size_t)e->L * e->B * 2 * e->R;
-    return upload(e, static_cast<char*>(e->Lh) + (size_t)first_sample * per * e->td, Lh, per * num_samples, (cudaStream_t)stream);
+    if (!e->tc_mode)
+        return upload(e, static_cast<char*>(e->Lh) + (size_t)first_sample * per * e->td, Lh, per * num_samples, (cudaStream_t)stream);
+    // tensor-core layout: fp16, tiled per 128 utterances, 128-byte rows pre-swizzled so that TMA drops them straight into
+    // an MMA operand tile (wn_tc_kernel.cu).  Host sources bounce through the staging buffer in whole samples.
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_device_ptr(Lh)) {
+        CK(wn_tc_cond_convert(e->Lh, Lh, first_sample, num_samples, e->L, e->B, st));
+        return 0;
+    }
+    const int chunk = (int)(e->stage_elems / per);
+    if (chunk < 1) return fail(NVWN_ENOMEM, "nvwn_set_conditioning: staging buffer smaller than one sample of conditioning");
+    for (int done = 0; done < num_samples; done += chunk) {
+        const int m = (num_samples - done < chunk) ? num_samples - done : chunk;
+        CK(cudaMemcpyAsync(e->stage_dev, Lh + (size_t)done * per, (size_t)m * per * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(wn_tc_cond_convert(e->Lh, e->stage_dev, first_sample + done, m, e->L, e->B, st));
+    }
+    return 0;
 }
 
 int nvwn_set_inputs(nvwn_engine* e, const float* Lh, const float* selectors)
@@ -355,7 +375,9 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
     WnParams p;
     fill_params(e, p, init_sample, count, num_samples, batch_size, dump_activations ? 1 : 0);
     if (count > 0) {
-        if (want_tc(e, batch_size)) {
+        if (e->tc_mode) {
+            if (batch_size != e->B)
+                return fail(NVWN_EINVAL, "nvwn_run_partial: the tensor-core path needs batch_size equal to the engine's batch size");
             if (e->tc_dirty) {
                 CK(wn_tc_pack(e->tc_image, p, stream));
                 e->tc_dirty = false;

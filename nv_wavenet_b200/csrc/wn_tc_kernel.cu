@@ -49,8 +49,38 @@ __host__ __device__ inline TcImage tc_image(int S, int L)
 
 __host__ __device__ inline size_t tc_smem_bytes(int S, int L, int nstage)
 {
-    // 4 activation tiles + ring + biases (Bh, Bres, Bskip-sum, Bzs, Bza) + barriers
-    return 1024 + 4 * (size_t)TILE + (size_t)nstage * TILE + ((size_t)L * 192 + S + 2 * A) * sizeof(float) + (2 * nstage + 8) * 8 + 16;
+    // 4 activation tiles + ring + 64x64 identity + biases (Bh, Bres, Bskip-sum, Bzs, Bza) + dilations + barriers
+    return 1024 + 4 * (size_t)TILE + (size_t)nstage * TILE + TILE / 2 + ((size_t)L * 192 + S + 2 * A) * sizeof(float) + (size_t)L * 4 +
+           (2 * nstage + 8) * 8 + 16;
+}
+
+// Conditioning in the tensor-core layout: fp16 [N][L][Bpad rows][2 halves of 64 channels], tiled per 128 utterances;
+// inside a tile: [half][row][128 B], 16-byte chunks XOR-swizzled with (row & 7) -- i.e. exactly the K-major
+// SWIZZLE_128B image of an MMA A-operand tile, so a 1-D bulk TMA copy of rows*128 bytes needs no further shuffling.
+__host__ __device__ inline int cond_rows(int B, int tile) { const int r = B - tile * 128; return r >= 128 ? 128 : ((r + 7) & ~7); }
+__host__ __device__ inline size_t cond_bpad(int B) { const int nt = (B + 127) / 128; return (size_t)(nt - 1) * 128 + cond_rows(B, nt - 1); }
+
+__global__ void tc_cond_kernel(unsigned char* __restrict__ dst, const float* __restrict__ src, int first_sample, int nsamples, int L, int B)
+{
+    // one thread per (sample, layer, utterance, 8-channel chunk): 32 B in, 16 B out
+    const size_t total = (size_t)nsamples * L * B * 16;
+    const size_t bpad = cond_bpad(B);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 15);
+        const size_t rowi = i >> 4;                       // (s * L + l) * B + b
+        const int b = (int)(rowi % B);
+        const size_t sl = rowi / B;                       // s * L + l
+        const float4 f0 = *reinterpret_cast<const float4*>(src + rowi * 128 + c * 8);
+        const float4 f1 = *reinterpret_cast<const float4*>(src + rowi * 128 + c * 8 + 4);
+        __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w), h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
+        uint4 o;
+        o.x = *reinterpret_cast<unsigned*>(&h0); o.y = *reinterpret_cast<unsigned*>(&h1);
+        o.z = *reinterpret_cast<unsigned*>(&h2); o.w = *reinterpret_cast<unsigned*>(&h3);
+        const int tile = b >> 7, r = b & 127, half = c >> 3, q = c & 7;
+        const size_t off = (((size_t)first_sample * L + sl) * bpad + (size_t)tile * 128) * 256 + (size_t)half * cond_rows(B, tile) * 128 +
+                           (size_t)r * 128 + (size_t)((q ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst + off) = o;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ pack
@@ -131,12 +161,14 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     unsigned char* t_h = smem + TILE;              // gated activation tile              (= BIG k-tile 1)
     unsigned char* t_big = smem;                   // [128 x 256] as 4 k-tiles: relu(skip) then relu(Zs)
     unsigned char* ring = smem + 4 * TILE;
-    float* s_bh = reinterpret_cast<float*>(ring + (size_t)nstage * TILE);
+    unsigned char* t_ident = ring + (size_t)nstage * TILE;     // 64 x 64 identity (B operand that injects Lh)
+    float* s_bh = reinterpret_cast<float*>(t_ident + TILE / 2);
     float* s_bres = s_bh + (size_t)L * 128;
     float* s_bsk = s_bres + (size_t)L * 64;
     float* s_bzs = s_bsk + S;
     float* s_bza = s_bzs + A;
-    uint64_t* w_full = reinterpret_cast<uint64_t*>(s_bza + A);
+    int* s_dil = reinterpret_cast<int*>(s_bza + A);
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(s_dil + L + (L & 1));
     uint64_t* w_empty = w_full + nstage;
     uint64_t* epi_done = w_empty + nstage;
     uint64_t* d1_full = epi_done + 1;
@@ -159,25 +191,36 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         mbar_init(epi_done, 128);
         mbar_init(d1_full, 1); mbar_init(dx_full, 1); mbar_init(skip_full, 1); mbar_init(out_full, 1);
         fence_mbar_init();
+        // dilation of layer l (nv_wavenet.cuh:99-111): 1,2,4..maxDil,1,2,...
+        int d = 1;
+        for (int l = 0; l < L; l++) { s_dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; }
     }
     if (warp == 4) tmem_alloc<512>(tmem_slot);
-    {   // biases -> shared memory
+    {   // biases and the identity tile -> shared memory
         const float* gb = reinterpret_cast<const float*>(img + im.off_bias);
         for (int i = tid; i < L * 128; i += NT) s_bh[i] = gb[im.b_bh + i];
         for (int i = tid; i < L * 64; i += NT) s_bres[i] = gb[im.b_bres + i];
         for (int i = tid; i < S; i += NT) s_bsk[i] = gb[im.b_bskp + (size_t)(L - 1) * S + i];
         for (int i = tid; i < A; i += NT) { s_bzs[i] = gb[im.b_bzs + i]; s_bza[i] = gb[im.b_bza + i]; }
+        for (int i = tid; i < TILE / 2 / 4; i += NT) reinterpret_cast<uint32_t*>(t_ident)[i] = 0u;
     }
+    __syncthreads();
+    if (tid < 64) *reinterpret_cast<__half*>(t_ident + sw128_offset(tid, tid)) = __float2half_rn(1.0f);
+    fence_proxy_async();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t D1 = tmem_base, DX = tmem_base + 128, DSKIP = tmem_base + 256, DZS = tmem_base + 256, DZA = tmem_base;
 
-    // dilation of layer l (nv_wavenet.cuh:99-111): 1,2,4..maxDil,1,2,...
-    int cyc = 0;
-    for (int d = 1; d <= p.maxDil; d <<= 1) cyc++;
-    auto dil = [&](int l) -> int { return 1 << (l % cyc); };
+    // conditioning tile geometry (see tc_cond_kernel)
+    const int c_rows = cond_rows(B, tile);
+    const uint32_t c_bytes = (uint32_t)c_rows * 128u;
+    const size_t c_bpad = cond_bpad(B);
+    const unsigned char* gcond = static_cast<const unsigned char*>(p.Lh);
+    auto cond_ptr = [&](int t, int l, int half) -> const unsigned char* {
+        return gcond + (((size_t)t * L + l) * c_bpad + (size_t)tile * 128) * 256 + (size_t)half * c_bytes;
+    };
 
     // debug timeline: role r (0 epilogue thread 0, 1 MMA issuer, 2 producer) appends (tag << 48 | clock) words
     unsigned long long* trc = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
@@ -198,8 +241,10 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             for (int t = t_begin; t < t_end; t++) {
                 for (int l = 0; l < L; l++) {
                     const unsigned char* lw = img + (size_t)l * im.layer_bytes;
-                    const int d = dil(l);
+                    const int d = s_dil[l];
                     TRACE(2, 100 + l);
+                    put(cond_ptr(t, l, 0), c_bytes);                     // Lh[t][l], channels 0..63 / 64..127 of this tile
+                    put(cond_ptr(t, l, 1), c_bytes);
                     if (t >= d) { put(ring_tile(t - d, l), TILE); put(lw, TILE); }
                     put(lw + TILE, TILE);
                     put(lw + 2 * TILE, TILE / 2);
@@ -215,77 +260,89 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
             int stage = 0;
             uint32_t ph_full = 0, ph_epi = 0;
-            const uint32_t ring_a = smem_u32(ring), xc_a = smem_u32(t_xc), h_a = smem_u32(t_h), big_a = smem_u32(t_big);
-            auto wait_stage = [&]() -> int {       // returns the stage index whose data has landed, advances
+            const uint64_t d_ring = make_desc_kmajor_sw128(smem_u32(ring)), d_xc = make_desc_kmajor_sw128(smem_u32(t_xc)),
+                           d_h = make_desc_kmajor_sw128(smem_u32(t_h)), d_big = make_desc_kmajor_sw128(smem_u32(t_big)),
+                           d_ident = make_desc_kmajor_sw128(smem_u32(t_ident));
+            constexpr uint64_t TILE_D = TILE >> 4;                      // one tile further, in descriptor address units
+            auto wait_stage = [&]() -> uint64_t {                       // descriptor of the next ring stage once its data landed
                 mbar_wait(&w_full[stage], ph_full);
-                const int s = stage;
-                if (++stage == nstage) { stage = 0; ph_full ^= 1; }
-                return s;
+                const uint64_t d = d_ring + (uint64_t)stage * TILE_D;
+                return d;
             };
-            auto mma4 = [&](uint32_t a_addr, uint32_t b_addr, uint32_t d, uint32_t idesc, bool acc0) {
-                const uint64_t da = make_desc_kmajor_sw128(a_addr), db = make_desc_kmajor_sw128(b_addr);
+            auto release_stage = [&]() {                                // frees the stage when the MMAs issued so far complete
+                umma_commit(&w_empty[stage]);
+                if (++stage == nstage) { stage = 0; ph_full ^= 1; }
+            };
+            auto mma4 = [&](uint64_t da, uint64_t db, uint32_t d, uint32_t idesc, bool acc0) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (acc0 || k) ? 1u : 0u);
             };
             auto wait_epi = [&]() { mbar_wait(epi_done, ph_epi); ph_epi ^= 1; tc_fence_after_sync(); };
-            auto prev = [&](int l) {               // D1 = Wprev . x[t-d]   (overwrites D1)
-                const int sa = wait_stage(), sb = wait_stage();
-                tc_fence_after_sync();
-                mma4(ring_a + sa * TILE, ring_a + sb * TILE, D1, idesc128, false);
-                umma_commit(&w_empty[sa]);
-                umma_commit(&w_empty[sb]);
+            // D1 = Lh[t][l] (through the identity), then += Wprev . x[t-d]; both operands come from the ring
+            auto open_layer = [&](int t, int l) {
+                for (int half = 0; half < 2; half++) {
+                    const uint64_t da = wait_stage();
+                    tc_fence_after_sync();
+                    mma4(da, d_ident, D1 + 64 * half, idesc64, false);
+                    release_stage();
+                }
+                if (t >= s_dil[l]) {
+                    const uint64_t da = wait_stage();
+                    const int sa = stage;
+                    if (++stage == nstage) { stage = 0; ph_full ^= 1; }
+                    const uint64_t db = wait_stage();
+                    tc_fence_after_sync();
+                    mma4(da, db, D1, idesc128, true);
+                    umma_commit(&w_empty[sa]);
+                    release_stage();
+                }
             };
             for (int t = t_begin; t < t_end; t++) {
                 const bool dump = p.dump && (t == t_end - 1);
                 for (int l = 0; l < L; l++) {
+                    uint64_t dw = 0;
+                    if (l > 0) dw = wait_stage();                       // Wcur_l is already in flight: wait for it before x_l
                     wait_epi();                                         // x_l tile ready (and, for l = 0, Dza consumed)
                     TRACE(1, 20);
-                    const bool has_prev = t >= dil(l);
-                    if (l == 0 && has_prev) prev(0);
-                    {   // D1 += Wcur . x[t]
-                        const int s = wait_stage();
-                        tc_fence_after_sync();
-                        mma4(xc_a, ring_a + s * TILE, D1, idesc128, has_prev);
-                        umma_commit(&w_empty[s]);
-                        umma_commit(d1_full);
-                        TRACE(1, 21);
-                    }
+                    if (l == 0) { open_layer(t, 0); dw = wait_stage(); }
+                    tc_fence_after_sync();
+                    mma4(d_xc, dw, D1, idesc128, true);                 // D1 += Wcur . x[t]
+                    umma_commit(d1_full);
+                    release_stage();
+                    TRACE(1, 21);
+                    dw = wait_stage();                                  // Wres_l
                     wait_epi();                                         // h tile ready, D1 consumed
                     TRACE(1, 22);
-                    {   // Dx = Wres . h
-                        const int s = wait_stage();
-                        tc_fence_after_sync();
-                        mma4(h_a, ring_a + s * TILE, DX, idesc64, false);
-                        umma_commit(&w_empty[s]);
-                        umma_commit(dx_full);
-                        TRACE(1, 23);
-                    }
+                    mma4(d_h, dw, DX, idesc64, false);                  // Dx = Wres . h
+                    umma_commit(dx_full);
+                    release_stage();
+                    TRACE(1, 23);
                     for (int c = 0; c < S / 128; c++) {                 // Dskip (+)= Wskip . h   (accumulates over layers)
-                        const int s = wait_stage();
+                        dw = wait_stage();
                         tc_fence_after_sync();
-                        mma4(h_a, ring_a + s * TILE, DSKIP + c * 128, idesc128, l > 0);
-                        umma_commit(&w_empty[s]);
+                        mma4(d_h, dw, DSKIP + c * 128, idesc128, l > 0);
+                        release_stage();
                     }
                     if (dump || l == L - 1) umma_commit(skip_full);
-                    if (l + 1 < L && t >= dil(l + 1)) prev(l + 1);      // off the critical path
+                    if (l + 1 < L) open_layer(t, l + 1);                // off the critical path
                     TRACE(1, 24);
                 }
                 wait_epi();                                             // relu(skip) tile ready
                 for (int kt = 0; kt < S / 64; kt++)
                     for (int nh = 0; nh < 2; nh++) {
-                        const int s = wait_stage();
+                        const uint64_t dw = wait_stage();
                         tc_fence_after_sync();
-                        mma4(big_a + kt * TILE, ring_a + s * TILE, DZS + nh * 128, idesc128, kt > 0);
-                        umma_commit(&w_empty[s]);
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS + nh * 128, idesc128, kt > 0);
+                        release_stage();
                     }
                 umma_commit(out_full);
                 wait_epi();                                             // relu(Zs) tile ready
                 for (int kt = 0; kt < A / 64; kt++)
                     for (int nh = 0; nh < 2; nh++) {
-                        const int s = wait_stage();
+                        const uint64_t dw = wait_stage();
                         tc_fence_after_sync();
-                        mma4(big_a + kt * TILE, ring_a + s * TILE, DZA + nh * 128, idesc128, kt > 0);
-                        umma_commit(&w_empty[s]);
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA + nh * 128, idesc128, kt > 0);
+                        release_stage();
                     }
                 umma_commit(out_full);
             }
@@ -299,26 +356,11 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         uint32_t ph_d1 = 0, ph_dx = 0, ph_skip = 0, ph_out = 0;
         const __half* embPrev = static_cast<const __half*>(p.embPrev);
         const __half* embCur = static_cast<const __half*>(p.embCur);
-        const __half* Lh = static_cast<const __half*>(p.Lh);
         const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
         int yp = valid ? p.yPrev[b] : 0, yc = valid ? p.yCur[b] : 0;
         float x[R];                                   // residual stream of this utterance (fp32)
-        uint32_t lh[64];                              // Lh[t][l][b][0:128] as packed fp16 pairs
-        auto lh_ptr = [&](int t, int l) -> const uint4* {
-            return reinterpret_cast<const uint4*>(Lh + (((size_t)t * L + l) * B + (valid ? b : 0)) * 128);
-        };
-        auto load_lh = [&](int t, int l) {
-            const uint4* src = lh_ptr(t, l);
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint4 v = ldg_nc_v4(src + i);
-                lh[4 * i] = v.x; lh[4 * i + 1] = v.y; lh[4 * i + 2] = v.z; lh[4 * i + 3] = v.w;
-            }
-        };
         // History ring (global, read back d samples later by TMA): written AFTER the barrier arrival that publishes the
-        // shared-memory tile, so that the proxy fence in front of that arrival never waits for global stores (or for the
-        // conditioning loads below).  The stores are fenced by the next stage's fence.proxy.async, long before any TMA
-        // read of them (>= one full sample later).
+        // shared-memory tile, then fenced towards the async proxy while this thread would be waiting for the MMA anyway.
         auto store_history = [&](unsigned char* grow) {
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -327,8 +369,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 for (int j = 0; j < 4; j++) o[j] = pack_h2(x[8 * q + 2 * j], x[8 * q + 2 * j + 1]);
                 *reinterpret_cast<uint4*>(grow + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
+            fence_proxy_async_global();
         };
-        if (t_begin < t_end) load_lh(t_begin, 0);
 
         for (int t = t_begin; t < t_end; t++) {
             const bool dump = p.dump && (t == t_end - 1);
@@ -354,42 +396,43 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
                 tc_fence_before_sync();
-                fence_proxy_async();
+                fence_proxy_async_smem();
                 mbar_arrive(epi_done);                                  // x_0 ready
                 if (tid == 0) TRACE(0, 1);
-                store_history(ring_tile(t, 0));                         // off the critical path (see store_history)
+                store_history(ring_tile(t, 0));
             }
 
             for (int l = 0; l < L; l++) {
-                // ---------------- gate: h = tanh(a[0:R]) * sigmoid(a[R:2R]),  a = D1 + Bh + Lh   (reference.cpp:67-80)
+                // ---------------- gate: h = tanh(a[0:R]) * sigmoid(a[R:2R]),  a = D1 + Bh  (D1 already holds
+                // Wprev.x[t-d] + Wcur.x[t] + Lh[t][l])   (reference.cpp:67-80)
                 mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
                 tc_fence_after_sync();
                 if (tid == 0) TRACE(0, 2);
                 const float* bh = s_bh + (size_t)l * 128;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    uint32_t ta[16], sa[16];
-                    tmem_ld16(D1 + lane_off + 16 * q, ta);
-                    tmem_ld16(D1 + lane_off + 64 + 16 * q, sa);
+                for (int hh = 0; hh < 2; hh++) {
+                    uint32_t ta[32], sa[32];
+                    tmem_ld32(D1 + lane_off + 32 * hh, ta);
+                    tmem_ld32(D1 + lane_off + 64 + 32 * hh, sa);
                     tmem_ld_wait();
-                    uint32_t hp[8];
+                    uint32_t hp[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const int r0 = 16 * q + j;
-                        const float2 lt = unpack_h2(lh[r0 >> 1]), ls = unpack_h2(lh[32 + (r0 >> 1)]);
+                    for (int j = 0; j < 32; j += 2) {
+                        const int r0 = 32 * hh + j;
                         const float2 bt = *reinterpret_cast<const float2*>(bh + r0), bs = *reinterpret_cast<const float2*>(bh + 64 + r0);
-                        const float a0 = __uint_as_float(ta[j]) + bt.x + lt.x, a1 = __uint_as_float(ta[j + 1]) + bt.y + lt.y;
-                        const float g0 = __uint_as_float(sa[j]) + bs.x + ls.x, g1 = __uint_as_float(sa[j + 1]) + bs.y + ls.y;
+                        const float a0 = __uint_as_float(ta[j]) + bt.x, a1 = __uint_as_float(ta[j + 1]) + bt.y;
+                        const float g0 = __uint_as_float(sa[j]) + bs.x, g1 = __uint_as_float(sa[j + 1]) + bs.y;
                         const float h0 = wn::tanhf_fast(a0) * wn::sigmoidf_fast(g0);
                         const float h1 = wn::tanhf_fast(a1) * wn::sigmoidf_fast(g1);
                         hp[j >> 1] = pack_h2(h0, h1);
                     }
-                    *reinterpret_cast<uint4*>(t_h + chunk_off(row, 2 * q)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                    *reinterpret_cast<uint4*>(t_h + chunk_off(row, 2 * q + 1)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        *reinterpret_cast<uint4*>(t_h + chunk_off(row, 4 * hh + q)) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
                 }
                 if (tid == 0) TRACE(0, 12);
                 tc_fence_before_sync();
-                fence_proxy_async();
+                fence_proxy_async_smem();
                 mbar_arrive(epi_done);                                  // h ready, D1 free
                 if (tid == 0) TRACE(0, 3);
                 // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
@@ -398,14 +441,14 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 if (tid == 0) TRACE(0, 4);
                 const float* br = s_bres + (size_t)l * 64;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    uint32_t v[16];
-                    tmem_ld16(DX + lane_off + 16 * q, v);
+                for (int hh = 0; hh < 2; hh++) {
+                    uint32_t v[32];
+                    tmem_ld32(DX + lane_off + 32 * hh, v);
                     tmem_ld_wait();
-                    uint32_t o[8];
+                    uint32_t o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const int r0 = 16 * q + j;
+                    for (int j = 0; j < 32; j += 2) {
+                        const int r0 = 32 * hh + j;
                         const float2 bb = *reinterpret_cast<const float2*>(br + r0);
                         float v0 = x[r0] + (__uint_as_float(v[j]) + bb.x), v1 = x[r0 + 1] + (__uint_as_float(v[j + 1]) + bb.y);
                         if (!valid) { v0 = 0.f; v1 = 0.f; }
@@ -414,29 +457,17 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         if (dump && valid) { p.xtOut[((size_t)l * B + b) * R + r0] = v0; p.xtOut[((size_t)l * B + b) * R + r0 + 1] = v1; }
                     }
                     if (l + 1 < L) {
-                        const uint4 o0 = make_uint4(o[0], o[1], o[2], o[3]), o1 = make_uint4(o[4], o[5], o[6], o[7]);
-                        *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 2 * q)) = o0;
-                        *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 2 * q + 1)) = o1;
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 4 * hh + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
                     }
                 }
                 if (l + 1 < L) {
                     tc_fence_before_sync();
-                    fence_proxy_async();
+                    fence_proxy_async_smem();
                     mbar_arrive(epi_done);                              // x_{l+1} ready
                     if (tid == 0) TRACE(0, 5);
                     store_history(ring_tile(t, l + 1));
-                }
-                // conditioning of the next layer (next sample when wrapping): issued here, consumed after the next MMA;
-                // the rows of the layer after that are pulled into L2 now
-                {
-                    const bool wrap = (l + 1 == L);
-                    const int tn = wrap ? t + 1 : t, ln = wrap ? 0 : l + 1;
-                    if (tn < t_end) {
-                        load_lh(tn, ln);
-                        const bool wrap2 = (ln + 1 == L);
-                        const int t2 = wrap2 ? tn + 1 : tn, l2 = wrap2 ? 0 : ln + 1;
-                        if (t2 < t_end) { prefetch_l2(lh_ptr(t2, l2)); prefetch_l2(reinterpret_cast<const char*>(lh_ptr(t2, l2)) + 128); }
-                    }
                 }
                 // ---------------- per-layer skip dump (last sample of a dumping launch only)
                 if (dump && l + 1 < L) {
@@ -477,7 +508,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
             }
             tc_fence_before_sync();
-            fence_proxy_async();
+            fence_proxy_async_smem();
             mbar_arrive(epi_done);                                      // relu(skip) tile ready
             if (tid == 0) TRACE(0, 7);
 
@@ -503,7 +534,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
             }
             tc_fence_before_sync();
-            fence_proxy_async();
+            fence_proxy_async_smem();
             mbar_arrive(epi_done);                                      // relu(Zs) tile ready
             if (tid == 0) TRACE(0, 9);
 
@@ -584,6 +615,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         if (valid) { p.yPrev[b] = yp; p.yCur[b] = yc; }
         tc_fence_before_sync();
     }
+#undef TRACE
 
     __syncthreads();
     if (warp == 4) tmem_dealloc<512>(tmem_base);
@@ -606,6 +638,18 @@ bool wn_tc_supported(int R_, int S, int A_, int L, int)
 size_t wn_tc_image_bytes(int, int S, int, int L) { return tc_image(S, L).total; }
 
 size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B) { return (size_t)(maxDil + 1) * L * ((B + 127) / 128) * TILE; }
+
+size_t wn_tc_cond_bytes(int L, int B, int N) { return (size_t)N * L * cond_bpad(B) * 256; }
+
+cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream)
+{
+    if (nsamples <= 0) return cudaSuccess;
+    const size_t total = (size_t)nsamples * L * B * 16;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    tc_cond_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<unsigned char*>(dst), src_dev, first_sample, nsamples, L, B);
+    return cudaGetLastError();
+}
 
 cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream)
 {
