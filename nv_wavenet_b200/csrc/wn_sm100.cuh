@@ -53,6 +53,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
+// one lane of a CONVERGED warp; lets the compiler feed tcgen05 / TMA operands from uniform registers directly
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------ fences
 // generic-proxy writes (st.shared / st.global) -> visible to the async proxy (TMA, tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }

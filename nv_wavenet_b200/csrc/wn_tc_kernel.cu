@@ -228,35 +228,39 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 #define TRACE(role, tag) do { if (trc && t == p.trace_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
 
     if (warp == 4) {
-        // =============================================================== TMA producer
-        if (lane == 0) {
+        // =============================================================== TMA producer (whole warp converged, one lane issues)
+        {
             int stage = 0;
             uint32_t ph = 1;
             auto put = [&](const void* src, uint32_t bytes) {
                 mbar_wait(&w_empty[stage], ph);
-                mbar_arrive_expect_tx(&w_full[stage], bytes);
-                tma_load_1d(ring + (size_t)stage * TILE, src, bytes, &w_full[stage]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&w_full[stage], bytes);
+                    tma_load_1d(ring + (size_t)stage * TILE, src, bytes, &w_full[stage]);
+                }
+                __syncwarp();
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
             };
             for (int t = t_begin; t < t_end; t++) {
+                int d = 1;
                 for (int l = 0; l < L; l++) {
                     const unsigned char* lw = img + (size_t)l * im.layer_bytes;
-                    const int d = s_dil[l];
-                    TRACE(2, 100 + l);
+                    if (lane == 0) TRACE(2, 100 + l);
                     put(cond_ptr(t, l, 0), c_bytes);                     // Lh[t][l], channels 0..63 / 64..127 of this tile
                     put(cond_ptr(t, l, 1), c_bytes);
                     if (t >= d) { put(ring_tile(t - d, l), TILE); put(lw, TILE); }
                     put(lw + TILE, TILE);
                     put(lw + 2 * TILE, TILE / 2);
                     for (int c = 0; c < S / 128; c++) put(lw + 2 * TILE + TILE / 2 + (size_t)c * TILE, TILE);
+                    d <<= 1; if (d > p.maxDil) d = 1;
                 }
                 const unsigned char* ow = img + im.off_out;
                 for (int c = 0; c < (S / 64) * 2 + (A / 64) * 2; c++) put(ow + (size_t)c * TILE, TILE);
             }
         }
     } else if (warp == 5) {
-        // =============================================================== MMA issuer
-        if (lane == 0) {
+        // =============================================================== MMA issuer (whole warp converged, one lane issues)
+        {
             const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
             int stage = 0;
             uint32_t ph_full = 0, ph_epi = 0;
@@ -266,85 +270,87 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             constexpr uint64_t TILE_D = TILE >> 4;                      // one tile further, in descriptor address units
             auto wait_stage = [&]() -> uint64_t {                       // descriptor of the next ring stage once its data landed
                 mbar_wait(&w_full[stage], ph_full);
-                const uint64_t d = d_ring + (uint64_t)stage * TILE_D;
-                return d;
+                return d_ring + (uint64_t)stage * TILE_D;
             };
-            auto release_stage = [&]() {                                // frees the stage when the MMAs issued so far complete
-                umma_commit(&w_empty[stage]);
-                if (++stage == nstage) { stage = 0; ph_full ^= 1; }
-            };
-            auto mma4 = [&](uint64_t da, uint64_t db, uint32_t d, uint32_t idesc, bool acc0) {
+            auto advance = [&]() { if (++stage == nstage) { stage = 0; ph_full ^= 1; } };
+            // 4 K-slices of one 64-deep chunk, then (optionally) up to two commits; single elected lane
+            auto mma4 = [&](uint64_t da, uint64_t db, uint32_t d, uint32_t idesc, bool acc0, uint64_t* bar0, uint64_t* bar1) {
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (acc0 || k) ? 1u : 0u);
+                    for (int k = 0; k < 4; k++) umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (acc0 || k) ? 1u : 0u);
+                    if (bar0) umma_commit(bar0);
+                    if (bar1) umma_commit(bar1);
+                }
+                __syncwarp();
             };
             auto wait_epi = [&]() { mbar_wait(epi_done, ph_epi); ph_epi ^= 1; tc_fence_after_sync(); };
             // D1 = Lh[t][l] (through the identity), then += Wprev . x[t-d]; both operands come from the ring
-            auto open_layer = [&](int t, int l) {
+            auto open_layer = [&](bool has_prev) {
                 for (int half = 0; half < 2; half++) {
                     const uint64_t da = wait_stage();
                     tc_fence_after_sync();
-                    mma4(da, d_ident, D1 + 64 * half, idesc64, false);
-                    release_stage();
+                    mma4(da, d_ident, D1 + 64 * half, idesc64, false, &w_empty[stage], nullptr);
+                    advance();
                 }
-                if (t >= s_dil[l]) {
+                if (has_prev) {
                     const uint64_t da = wait_stage();
                     const int sa = stage;
-                    if (++stage == nstage) { stage = 0; ph_full ^= 1; }
+                    advance();
                     const uint64_t db = wait_stage();
                     tc_fence_after_sync();
-                    mma4(da, db, D1, idesc128, true);
-                    umma_commit(&w_empty[sa]);
-                    release_stage();
+                    mma4(da, db, D1, idesc128, true, &w_empty[sa], &w_empty[stage]);
+                    advance();
                 }
             };
             for (int t = t_begin; t < t_end; t++) {
                 const bool dump = p.dump && (t == t_end - 1);
+                int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
                 for (int l = 0; l < L; l++) {
+                    int dn = d << 1; if (dn > p.maxDil) dn = 1;         // dilation of layer l + 1
                     uint64_t dw = 0;
                     if (l > 0) dw = wait_stage();                       // Wcur_l is already in flight: wait for it before x_l
                     wait_epi();                                         // x_l tile ready (and, for l = 0, Dza consumed)
-                    TRACE(1, 20);
-                    if (l == 0) { open_layer(t, 0); dw = wait_stage(); }
+                    if (lane == 0) TRACE(1, 20);
+                    if (l == 0) { open_layer(t >= d); dw = wait_stage(); }
                     tc_fence_after_sync();
-                    mma4(d_xc, dw, D1, idesc128, true);                 // D1 += Wcur . x[t]
-                    umma_commit(d1_full);
-                    release_stage();
-                    TRACE(1, 21);
+                    mma4(d_xc, dw, D1, idesc128, true, d1_full, &w_empty[stage]);      // D1 += Wcur . x[t]
+                    advance();
+                    if (lane == 0) TRACE(1, 21);
                     dw = wait_stage();                                  // Wres_l
                     wait_epi();                                         // h tile ready, D1 consumed
-                    TRACE(1, 22);
-                    mma4(d_h, dw, DX, idesc64, false);                  // Dx = Wres . h
-                    umma_commit(dx_full);
-                    release_stage();
-                    TRACE(1, 23);
+                    if (lane == 0) TRACE(1, 22);
+                    mma4(d_h, dw, DX, idesc64, false, dx_full, &w_empty[stage]);        // Dx = Wres . h
+                    advance();
+                    if (lane == 0) TRACE(1, 23);
                     for (int c = 0; c < S / 128; c++) {                 // Dskip (+)= Wskip . h   (accumulates over layers)
                         dw = wait_stage();
                         tc_fence_after_sync();
-                        mma4(d_h, dw, DSKIP + c * 128, idesc128, l > 0);
-                        release_stage();
+                        const bool last = (c == S / 128 - 1) && (dump || l == L - 1);
+                        mma4(d_h, dw, DSKIP + c * 128, idesc128, l > 0, &w_empty[stage], last ? skip_full : nullptr);
+                        advance();
                     }
-                    if (dump || l == L - 1) umma_commit(skip_full);
-                    if (l + 1 < L) open_layer(t, l + 1);                // off the critical path
-                    TRACE(1, 24);
+                    if (l + 1 < L) open_layer(t >= dn);                 // off the critical path
+                    if (lane == 0) TRACE(1, 24);
+                    d = dn;
                 }
                 wait_epi();                                             // relu(skip) tile ready
                 for (int kt = 0; kt < S / 64; kt++)
                     for (int nh = 0; nh < 2; nh++) {
                         const uint64_t dw = wait_stage();
                         tc_fence_after_sync();
-                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS + nh * 128, idesc128, kt > 0);
-                        release_stage();
+                        const bool last = (kt == S / 64 - 1) && nh == 1;
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
+                        advance();
                     }
-                umma_commit(out_full);
                 wait_epi();                                             // relu(Zs) tile ready
                 for (int kt = 0; kt < A / 64; kt++)
                     for (int nh = 0; nh < 2; nh++) {
                         const uint64_t dw = wait_stage();
                         tc_fence_after_sync();
-                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA + nh * 128, idesc128, kt > 0);
-                        release_stage();
+                        const bool last = (kt == A / 64 - 1) && nh == 1;
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
+                        advance();
                     }
-                umma_commit(out_full);
             }
         }
     } else {
