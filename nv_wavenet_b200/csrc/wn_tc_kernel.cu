@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     const TcImage im = tc_image(S, L);
 
     unsigned char* t_xc = smem;                    // x tile of the current layer        (= BIG k-tile 0)
-    unsigned char* t_h = smem + TILE;              // gated activation tile              (= BIG k-tile 1)
-    unsigned char* t_big = smem;                   // [128 x 256] as 4 k-tiles: relu(skip) then relu(Zs)
+    unsigned char* t_h = smem + TILE;              // gated activation tiles, double buffered by layer parity (= BIG k-tiles 1, 2)
+    unsigned char* t_big = smem;                   // [128 x 256] as 4 k-tiles: relu(skip), relu(Zs), then fp16 logits scratch
     unsigned char* ring = smem + 4 * TILE;
     unsigned char* t_ident = ring + (size_t)nstage * TILE;     // 64 x 64 identity (B operand that injects Lh)
     float* s_bh = reinterpret_cast<float*>(t_ident + TILE / 2);
@@ -211,7 +211,10 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t D1 = tmem_base, DX = tmem_base + 128, DSKIP = tmem_base + 256, DZS = tmem_base + 256, DZA = tmem_base;
+    // TMEM columns: [0,128) and [128,256) = pre-activation accumulators, ping-pong by layer parity; the residual GEMM of
+    // layer l writes columns [0,64) of the buffer the gate of layer l has just drained; [256,512) = skip sum over layers
+    // (then Zs); Za reuses [0,256).
+    const uint32_t D1B = tmem_base, DSKIP = tmem_base + 256, DZS = tmem_base + 256, DZA = tmem_base;
 
     // conditioning tile geometry (see tc_cond_kernel)
     const int c_rows = cond_rows(B, tile);
@@ -241,19 +244,31 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
             };
+            // Chunk order = consumption order of the MMA issuer (see there):
+            //   open(0) | cur(0) open(1) res(0) | cur(1) skip(0) open(2) res(1) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
+            // where open(l) = Lh[t][l] (two halves) and, if t >= d_l, the x[t-d_l] history tile + Wprev_l.
+            auto put_open = [&](int t, int l, int d) {
+                put(cond_ptr(t, l, 0), c_bytes);
+                put(cond_ptr(t, l, 1), c_bytes);
+                if (t >= d) { put(ring_tile(t - d, l), TILE); put(img + (size_t)l * im.layer_bytes, TILE); }
+            };
+            auto put_skip = [&](int l) {
+                for (int c = 0; c < S / 128; c++) put(img + (size_t)l * im.layer_bytes + 2 * TILE + TILE / 2 + (size_t)c * TILE, TILE);
+            };
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;
+                put_open(t, 0, 1);
                 for (int l = 0; l < L; l++) {
                     const unsigned char* lw = img + (size_t)l * im.layer_bytes;
+                    int dn = d << 1; if (dn > p.maxDil) dn = 1;
                     if (lane == 0) TRACE(2, 100 + l);
-                    put(cond_ptr(t, l, 0), c_bytes);                     // Lh[t][l], channels 0..63 / 64..127 of this tile
-                    put(cond_ptr(t, l, 1), c_bytes);
-                    if (t >= d) { put(ring_tile(t - d, l), TILE); put(lw, TILE); }
-                    put(lw + TILE, TILE);
-                    put(lw + 2 * TILE, TILE / 2);
-                    for (int c = 0; c < S / 128; c++) put(lw + 2 * TILE + TILE / 2 + (size_t)c * TILE, TILE);
-                    d <<= 1; if (d > p.maxDil) d = 1;
+                    put(lw + TILE, TILE);                               // Wcur_l
+                    if (l > 0) put_skip(l - 1);
+                    if (l + 1 < L) put_open(t, l + 1, dn);
+                    put(lw + 2 * TILE, TILE / 2);                       // Wres_l
+                    d = dn;
                 }
+                put_skip(L - 1);
                 const unsigned char* ow = img + im.off_out;
                 for (int c = 0; c < (S / 64) * 2 + (A / 64) * 2; c++) put(ow + (size_t)c * TILE, TILE);
             }
@@ -284,12 +299,13 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
             };
             auto wait_epi = [&]() { mbar_wait(epi_done, ph_epi); ph_epi ^= 1; tc_fence_after_sync(); };
-            // D1 = Lh[t][l] (through the identity), then += Wprev . x[t-d]; both operands come from the ring
-            auto open_layer = [&](bool has_prev) {
+            // open(l): D1[l&1] = Lh[t][l] (through the identity), then += Wprev_l . x[t-d]; all operands come from the ring
+            auto open_layer = [&](int l, bool has_prev) {
+                const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128;
                 for (int half = 0; half < 2; half++) {
                     const uint64_t da = wait_stage();
                     tc_fence_after_sync();
-                    mma4(da, d_ident, D1 + 64 * half, idesc64, false, &w_empty[stage], nullptr);
+                    mma4(da, d_ident, d1 + 64 * half, idesc64, false, &w_empty[stage], nullptr);
                     advance();
                 }
                 if (has_prev) {
@@ -298,41 +314,49 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     advance();
                     const uint64_t db = wait_stage();
                     tc_fence_after_sync();
-                    mma4(da, db, D1, idesc128, true, &w_empty[sa], &w_empty[stage]);
+                    mma4(da, db, d1, idesc128, true, &w_empty[sa], &w_empty[stage]);
                     advance();
                 }
             };
+            // skip(l): Dskip (+)= Wskip_l . h_l, h_l in the H buffer of parity l
+            auto skip_layer = [&](int l, uint64_t* done_bar) {
+                const uint64_t dh = d_h + (uint64_t)(l & 1) * TILE_D;
+                for (int c = 0; c < S / 128; c++) {
+                    const uint64_t dw = wait_stage();
+                    tc_fence_after_sync();
+                    mma4(dh, dw, DSKIP + c * 128, idesc128, l > 0, &w_empty[stage], (c == S / 128 - 1) ? done_bar : nullptr);
+                    advance();
+                }
+            };
+            // Issue order per layer: cur(l) | skip(l-1), open(l+1) in the shadow of the gate epilogue | res(l).
+            // The residual epilogue therefore runs with the tensor pipe idle, and nothing but cur / res sits between
+            // an epilogue arrival and the accumulator it waits for.
             for (int t = t_begin; t < t_end; t++) {
-                const bool dump = p.dump && (t == t_end - 1);
                 int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
                 for (int l = 0; l < L; l++) {
                     int dn = d << 1; if (dn > p.maxDil) dn = 1;         // dilation of layer l + 1
+                    const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128;
                     uint64_t dw = 0;
                     if (l > 0) dw = wait_stage();                       // Wcur_l is already in flight: wait for it before x_l
                     wait_epi();                                         // x_l tile ready (and, for l = 0, Dza consumed)
                     if (lane == 0) TRACE(1, 20);
-                    if (l == 0) { open_layer(t >= d); dw = wait_stage(); }
+                    if (l == 0) { open_layer(0, t >= 1); dw = wait_stage(); }
                     tc_fence_after_sync();
-                    mma4(d_xc, dw, D1, idesc128, true, d1_full, &w_empty[stage]);      // D1 += Wcur . x[t]
+                    mma4(d_xc, dw, d1, idesc128, true, d1_full, &w_empty[stage]);       // D1 += Wcur . x[t]
                     advance();
                     if (lane == 0) TRACE(1, 21);
+                    if (l > 0) skip_layer(l - 1, nullptr);
+                    if (l + 1 < L) open_layer(l + 1, t >= dn);
+                    if (lane == 0) TRACE(1, 24);
                     dw = wait_stage();                                  // Wres_l
                     wait_epi();                                         // h tile ready, D1 consumed
                     if (lane == 0) TRACE(1, 22);
-                    mma4(d_h, dw, DX, idesc64, false, dx_full, &w_empty[stage]);        // Dx = Wres . h
+                    mma4(d_h + (uint64_t)(l & 1) * TILE_D, dw, d1, idesc64, false, dx_full, &w_empty[stage]);   // Dx = Wres . h
                     advance();
                     if (lane == 0) TRACE(1, 23);
-                    for (int c = 0; c < S / 128; c++) {                 // Dskip (+)= Wskip . h   (accumulates over layers)
-                        dw = wait_stage();
-                        tc_fence_after_sync();
-                        const bool last = (c == S / 128 - 1) && (dump || l == L - 1);
-                        mma4(d_h, dw, DSKIP + c * 128, idesc128, l > 0, &w_empty[stage], last ? skip_full : nullptr);
-                        advance();
-                    }
-                    if (l + 1 < L) open_layer(t >= dn);                 // off the critical path
-                    if (lane == 0) TRACE(1, 24);
                     d = dn;
                 }
+                skip_layer(L - 1, skip_full);
                 wait_epi();                                             // relu(skip) tile ready
                 for (int kt = 0; kt < S / 64; kt++)
                     for (int nh = 0; nh < 2; nh++) {
@@ -358,6 +382,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         const int row = tid;
         const int b = tile * 128 + row;
         const bool valid = b < B;
+        const bool wv = tile * 128 + warp * 32 < B;     // warp has at least one live utterance: dead warps only keep the
+                                                        // barrier protocol going (their rows of every tile are never read back)
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         uint32_t ph_d1 = 0, ph_dx = 0, ph_skip = 0, ph_out = 0;
         const __half* embPrev = static_cast<const __half*>(p.embPrev);
@@ -365,6 +391,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
         int yp = valid ? p.yPrev[b] : 0, yc = valid ? p.yCur[b] : 0;
         float x[R];                                   // residual stream of this utterance (fp32)
+#pragma unroll
+        for (int i = 0; i < R; i++) x[i] = 0.f;
         // History ring (global, read back d samples later by TMA): written AFTER the barrier arrival that publishes the
         // shared-memory tile, then fenced towards the async proxy while this thread would be waiting for the MMA anyway.
         auto store_history = [&](unsigned char* grow) {
@@ -377,12 +405,17 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             }
             fence_proxy_async_global();
         };
+        auto publish = [&]() {                         // smem tile written -> visible to the MMA (async proxy), then signal
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+            mbar_arrive(epi_done);
+        };
 
         for (int t = t_begin; t < t_end; t++) {
             const bool dump = p.dump && (t == t_end - 1);
             const float sel = valid ? __ldg(p.sel + (size_t)t * B + b) : 0.5f;
             // ---------------- embedding: x0 = tanh(embPrev[yPrev] + embCur[yCur])   (reference.cpp:42-57)
-            {
+            if (wv) {
                 const uint4* ep = reinterpret_cast<const uint4*>(embPrev + (size_t)yp * R);
                 const uint4* ec = reinterpret_cast<const uint4*>(embCur + (size_t)yc * R);
 #pragma unroll
@@ -401,93 +434,91 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     }
                     *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
-                tc_fence_before_sync();
-                fence_proxy_async_smem();
-                mbar_arrive(epi_done);                                  // x_0 ready
-                if (tid == 0) TRACE(0, 1);
-                store_history(ring_tile(t, 0));
             }
+            publish();                                                  // x_0 ready
+            if (tid == 0) TRACE(0, 1);
+            if (wv) store_history(ring_tile(t, 0));
 
             for (int l = 0; l < L; l++) {
+                const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128 + lane_off;
+                unsigned char* th = t_h + (size_t)(l & 1) * TILE;
                 // ---------------- gate: h = tanh(a[0:R]) * sigmoid(a[R:2R]),  a = D1 + Bh  (D1 already holds
                 // Wprev.x[t-d] + Wcur.x[t] + Lh[t][l])   (reference.cpp:67-80)
                 mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
                 tc_fence_after_sync();
                 if (tid == 0) TRACE(0, 2);
-                const float* bh = s_bh + (size_t)l * 128;
+                if (wv) {
+                    const float* bh = s_bh + (size_t)l * 128;
 #pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    uint32_t ta[32], sa[32];
-                    tmem_ld32(D1 + lane_off + 32 * hh, ta);
-                    tmem_ld32(D1 + lane_off + 64 + 32 * hh, sa);
-                    tmem_ld_wait();
-                    uint32_t hp[16];
+                    for (int hh = 0; hh < 2; hh++) {
+                        uint32_t ta[32], sa[32];
+                        tmem_ld32(d1 + 32 * hh, ta);
+                        tmem_ld32(d1 + 64 + 32 * hh, sa);
+                        tmem_ld_wait();
+                        uint32_t hp[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int r0 = 32 * hh + j;
-                        const float2 bt = *reinterpret_cast<const float2*>(bh + r0), bs = *reinterpret_cast<const float2*>(bh + 64 + r0);
-                        const float a0 = __uint_as_float(ta[j]) + bt.x, a1 = __uint_as_float(ta[j + 1]) + bt.y;
-                        const float g0 = __uint_as_float(sa[j]) + bs.x, g1 = __uint_as_float(sa[j + 1]) + bs.y;
-                        const float h0 = wn::tanhf_fast(a0) * wn::sigmoidf_fast(g0);
-                        const float h1 = wn::tanhf_fast(a1) * wn::sigmoidf_fast(g1);
-                        hp[j >> 1] = pack_h2(h0, h1);
+                        for (int j = 0; j < 32; j += 2) {
+                            const int r0 = 32 * hh + j;
+                            const float2 bt = *reinterpret_cast<const float2*>(bh + r0), bs = *reinterpret_cast<const float2*>(bh + 64 + r0);
+                            const float a0 = __uint_as_float(ta[j]) + bt.x, a1 = __uint_as_float(ta[j + 1]) + bt.y;
+                            const float g0 = __uint_as_float(sa[j]) + bs.x, g1 = __uint_as_float(sa[j + 1]) + bs.y;
+                            const float h0 = wn::tanhf_fast(a0) * wn::sigmoidf_fast(g0);
+                            const float h1 = wn::tanhf_fast(a1) * wn::sigmoidf_fast(g1);
+                            hp[j >> 1] = pack_h2(h0, h1);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            *reinterpret_cast<uint4*>(th + chunk_off(row, 4 * hh + q)) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        *reinterpret_cast<uint4*>(t_h + chunk_off(row, 4 * hh + q)) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
                 }
                 if (tid == 0) TRACE(0, 12);
-                tc_fence_before_sync();
-                fence_proxy_async_smem();
-                mbar_arrive(epi_done);                                  // h ready, D1 free
+                publish();                                              // h ready, D1 drained
                 if (tid == 0) TRACE(0, 3);
                 // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
                 mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
                 tc_fence_after_sync();
                 if (tid == 0) TRACE(0, 4);
-                const float* br = s_bres + (size_t)l * 64;
+                if (wv) {
+                    const float* br = s_bres + (size_t)l * 64;
 #pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    uint32_t v[32];
-                    tmem_ld32(DX + lane_off + 32 * hh, v);
-                    tmem_ld_wait();
-                    uint32_t o[16];
+                    for (int hh = 0; hh < 2; hh++) {
+                        uint32_t v[32];
+                        tmem_ld32(d1 + 32 * hh, v);
+                        tmem_ld_wait();
+                        uint32_t o[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int r0 = 32 * hh + j;
-                        const float2 bb = *reinterpret_cast<const float2*>(br + r0);
-                        float v0 = x[r0] + (__uint_as_float(v[j]) + bb.x), v1 = x[r0 + 1] + (__uint_as_float(v[j + 1]) + bb.y);
-                        if (!valid) { v0 = 0.f; v1 = 0.f; }
-                        x[r0] = v0; x[r0 + 1] = v1;
-                        o[j >> 1] = pack_h2(v0, v1);
-                        if (dump && valid) { p.xtOut[((size_t)l * B + b) * R + r0] = v0; p.xtOut[((size_t)l * B + b) * R + r0 + 1] = v1; }
+                        for (int j = 0; j < 32; j += 2) {
+                            const int r0 = 32 * hh + j;
+                            const float2 bb = *reinterpret_cast<const float2*>(br + r0);
+                            float v0 = x[r0] + (__uint_as_float(v[j]) + bb.x), v1 = x[r0 + 1] + (__uint_as_float(v[j + 1]) + bb.y);
+                            if (!valid) { v0 = 0.f; v1 = 0.f; }
+                            x[r0] = v0; x[r0 + 1] = v1;
+                            o[j >> 1] = pack_h2(v0, v1);
+                            if (dump && valid) { p.xtOut[((size_t)l * B + b) * R + r0] = v0; p.xtOut[((size_t)l * B + b) * R + r0 + 1] = v1; }
+                        }
+                        if (l + 1 < L) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 4 * hh + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                        }
                     }
-                    if (l + 1 < L) {
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 4 * hh + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
+                    // next contribution is only issued after the arrival below: the per-layer dump needs no extra barrier
+                    if (dump && l > 0) {
+                        for (int c0 = 0; c0 < S; c0 += 16) {
+                            uint32_t v[16];
+                            tmem_ld16(DSKIP + lane_off + c0, v);
+                            tmem_ld_wait();
+                            if (valid)
+                                for (int j = 0; j < 16; j++)
+                                    p.skipOut[((size_t)(l - 1) * B + b) * S + c0 + j] = __uint_as_float(v[j]) + gbias[im.b_bskp + (size_t)(l - 1) * S + c0 + j];
+                        }
                     }
                 }
                 if (l + 1 < L) {
-                    tc_fence_before_sync();
-                    fence_proxy_async_smem();
-                    mbar_arrive(epi_done);                              // x_{l+1} ready
+                    publish();                                          // x_{l+1} ready
                     if (tid == 0) TRACE(0, 5);
-                    store_history(ring_tile(t, l + 1));
-                }
-                // ---------------- per-layer skip dump (last sample of a dumping launch only)
-                if (dump && l + 1 < L) {
-                    mbar_wait(skip_full, ph_skip); ph_skip ^= 1;
-                    tc_fence_after_sync();
-                    for (int c0 = 0; c0 < S; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(DSKIP + lane_off + c0, v);
-                        tmem_ld_wait();
-                        if (valid)
-                            for (int j = 0; j < 16; j++)
-                                p.skipOut[((size_t)l * B + b) * S + c0 + j] = __uint_as_float(v[j]) + gbias[im.b_bskp + (size_t)l * S + c0 + j];
-                    }
-                    tc_fence_before_sync();
+                    if (wv) store_history(ring_tile(t, l + 1));
                 }
             }
 
@@ -495,116 +526,141 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             mbar_wait(skip_full, ph_skip); ph_skip ^= 1;
             tc_fence_after_sync();
             if (tid == 0) TRACE(0, 6);
+            if (wv) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < S; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(DSKIP + lane_off + c0, v);
-                tmem_ld_wait();
-                uint32_t o[8];
+                for (int c0 = 0; c0 < S; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(DSKIP + lane_off + c0, v);
+                    tmem_ld_wait();
+                    uint32_t o[8];
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    float v0 = fmaxf(__uint_as_float(v[j]) + s_bsk[c0 + j], 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + s_bsk[c0 + j + 1], 0.f);
-                    if (!valid) { v0 = 0.f; v1 = 0.f; }
-                    o[j >> 1] = pack_h2(v0, v1);
-                    if (dump && valid) { p.skipOut[((size_t)(L - 1) * B + b) * S + c0 + j] = v0; p.skipOut[((size_t)(L - 1) * B + b) * S + c0 + j + 1] = v1; }
+                    for (int j = 0; j < 16; j += 2) {
+                        float v0 = fmaxf(__uint_as_float(v[j]) + s_bsk[c0 + j], 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + s_bsk[c0 + j + 1], 0.f);
+                        if (!valid) { v0 = 0.f; v1 = 0.f; }
+                        o[j >> 1] = pack_h2(v0, v1);
+                        if (dump && valid) { p.skipOut[((size_t)(L - 1) * B + b) * S + c0 + j] = v0; p.skipOut[((size_t)(L - 1) * B + b) * S + c0 + j + 1] = v1; }
+                    }
+                    unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
+                    const int q = (c0 & 63) >> 3;
+                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
                 }
-                unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
-                const int q = (c0 & 63) >> 3;
-                *reinterpret_cast<uint4*>(kt + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
             }
-            tc_fence_before_sync();
-            fence_proxy_async_smem();
-            mbar_arrive(epi_done);                                      // relu(skip) tile ready
+            publish();                                                  // relu(skip) tile ready
             if (tid == 0) TRACE(0, 7);
 
             // ---------------- Zs = relu(Wzs . skip + Bzs)   (reference.cpp:96-98)
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
+            if (wv) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < A; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(DZS + lane_off + c0, v);
-                tmem_ld_wait();
-                uint32_t o[8];
+                for (int c0 = 0; c0 < A; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(DZS + lane_off + c0, v);
+                    tmem_ld_wait();
+                    uint32_t o[8];
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    float v0 = fmaxf(__uint_as_float(v[j]) + s_bzs[c0 + j], 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + s_bzs[c0 + j + 1], 0.f);
-                    if (!valid) { v0 = 0.f; v1 = 0.f; }
-                    o[j >> 1] = pack_h2(v0, v1);
-                    if (dump && valid) { p.Zs[(size_t)b * A + c0 + j] = v0; p.Zs[(size_t)b * A + c0 + j + 1] = v1; }
+                    for (int j = 0; j < 16; j += 2) {
+                        float v0 = fmaxf(__uint_as_float(v[j]) + s_bzs[c0 + j], 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + s_bzs[c0 + j + 1], 0.f);
+                        if (!valid) { v0 = 0.f; v1 = 0.f; }
+                        o[j >> 1] = pack_h2(v0, v1);
+                        if (dump && valid) { p.Zs[(size_t)b * A + c0 + j] = v0; p.Zs[(size_t)b * A + c0 + j + 1] = v1; }
+                    }
+                    unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
+                    const int q = (c0 & 63) >> 3;
+                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
                 }
-                unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
-                const int q = (c0 & 63) >> 3;
-                *reinterpret_cast<uint4*>(kt + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
             }
-            tc_fence_before_sync();
-            fence_proxy_async_smem();
-            mbar_arrive(epi_done);                                      // relu(Zs) tile ready
+            publish();                                                  // relu(Zs) tile ready
             if (tid == 0) TRACE(0, 9);
 
             // ---------------- Za, softmax, categorical sample -- all inside this thread   (reference.cpp:100-121)
+            // TMEM -> register bandwidth is the scarce resource: the logits are read from TMEM ONCE, parked as fp16 in this
+            // thread's own row of the (now dead) activation tiles, and the exp / scan passes run from shared memory.
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
             if (tid == 0) TRACE(0, 10);
-            float mx = 0.f;                                             // matrix.cpp:171 starts the max at 0
-#pragma unroll 1
-            for (int c0 = 0; c0 < A; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(DZA + lane_off + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; j++) mx = fmaxf(mx, __uint_as_float(v[j]) + s_bza[c0 + j]);
-            }
-            float csum[A / 16];
-            float total = 0.f;
-#pragma unroll
-            for (int c = 0; c < A / 16; c++) {
-                uint32_t v[16];
-                tmem_ld16(DZA + lane_off + 16 * c, v);
-                tmem_ld_wait();
-                float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; j++) s += wn::exp2f_fast((__uint_as_float(v[j]) + s_bza[16 * c + j] - mx) * 1.4426950408889634f);
-                csum[c] = s;
-                total += s;
-            }
-            const float target = sel * total;
-            int cb = A / 16 - 1;
-            float base = 0.f;
-            {
-                float run = 0.f;
-                bool found = false;
-#pragma unroll
-                for (int c = 0; c < A / 16; c++) {
-                    if (!found && target < run + csum[c]) { cb = c; base = run; found = true; }
-                    run += csum[c];
-                }
-                if (!found) base = run - csum[A / 16 - 1];
-            }
-            // third pass: every lane walks all chunks (tcgen05.ld is warp-collective: uniform address, no divergence
-            // around it) and scans only inside its own chunk `cb`; the dump of Za / P rides along
             int y = A - 1;
-            {
-                const float inv = 1.f / total;
-                bool found = false;
+            if (wv) {
+                float mx = 0.f;                                         // matrix.cpp:171 starts the max at 0
 #pragma unroll 1
-                for (int c = 0; c < A / 16; c++) {
+                for (int c0 = 0; c0 < A; c0 += 16) {
                     uint32_t v[16];
-                    tmem_ld16(DZA + lane_off + 16 * c, v);
+                    tmem_ld16(DZA + lane_off + c0, v);
                     tmem_ld_wait();
-                    if (c == cb || dump) {
-                        float run = base;
+                    uint32_t o[8];
 #pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        const float z0 = __uint_as_float(v[j]) + s_bza[c0 + j], z1 = __uint_as_float(v[j + 1]) + s_bza[c0 + j + 1];
+                        mx = fmaxf(mx, fmaxf(z0, z1));
+                        o[j >> 1] = pack_h2(z0, z1);
+                        if (dump && valid) { p.Za[(size_t)b * A + c0 + j] = z0; p.Za[(size_t)b * A + c0 + j + 1] = z1; }
+                    }
+                    unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
+                    const int q = (c0 & 63) >> 3;
+                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+                const float mxs = mx * 1.4426950408889634f;
+                auto expz = [&](uint32_t packed, float& e0, float& e1) {
+                    const float2 z = unpack_h2(packed);
+                    e0 = wn::exp2f_fast(fmaf(z.x, 1.4426950408889634f, -mxs));
+                    e1 = wn::exp2f_fast(fmaf(z.y, 1.4426950408889634f, -mxs));
+                };
+                float csum[A / 16];
+                float total = 0.f;
+#pragma unroll
+                for (int c = 0; c < A / 16; c++) {
+                    const unsigned char* kt = t_big + (size_t)(c >> 2) * TILE;
+                    const int q = (c & 3) * 2;
+                    const uint4 u0 = *reinterpret_cast<const uint4*>(kt + chunk_off(row, q)), u1 = *reinterpret_cast<const uint4*>(kt + chunk_off(row, q + 1));
+                    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { float e0, e1; expz(w[j], e0, e1); s += e0; s += e1; }
+                    csum[c] = s;
+                    total += s;
+                }
+                const float target = sel * total;
+                int cb = A / 16 - 1;
+                float base = 0.f;
+                {
+                    float run = 0.f;
+                    bool found = false;
+#pragma unroll
+                    for (int c = 0; c < A / 16; c++) {
+                        if (!found && target < run + csum[c]) { cb = c; base = run; found = true; }
+                        run += csum[c];
+                    }
+                    if (!found) base = run - csum[A / 16 - 1];
+                }
+                {   // scan inside the chosen 16-logit chunk (own row, own chunk: plain shared-memory reads)
+                    const unsigned char* kt = t_big + (size_t)(cb >> 2) * TILE;
+                    const int q = (cb & 3) * 2;
+                    const uint4 u0 = *reinterpret_cast<const uint4*>(kt + chunk_off(row, q)), u1 = *reinterpret_cast<const uint4*>(kt + chunk_off(row, q + 1));
+                    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                    float run = base;
+                    bool found = false;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float e0, e1;
+                        expz(w[j], e0, e1);
+                        run += e0;
+                        if (!found && target < run) { y = 16 * cb + 2 * j; found = true; }
+                        run += e1;
+                        if (!found && target < run) { y = 16 * cb + 2 * j + 1; found = true; }
+                    }
+                    if (!found) y = (cb == A / 16 - 1) ? A - 1 : 16 * cb + 15;
+                }
+                if (dump && valid) {
+                    const float inv = 1.f / total;
+                    for (int c = 0; c < A / 16; c++) {
+                        const unsigned char* kt = t_big + (size_t)(c >> 2) * TILE;
+                        const int q = (c & 3) * 2;
                         for (int j = 0; j < 16; j++) {
-                            const float z = __uint_as_float(v[j]) + s_bza[16 * c + j];
-                            const float e = wn::exp2f_fast((z - mx) * 1.4426950408889634f);
-                            if (c == cb) {
-                                run += e;
-                                if (!found && target < run) { y = 16 * c + j; found = true; }
-                            }
-                            if (dump && valid) { p.Za[(size_t)b * A + 16 * c + j] = z; p.P[(size_t)b * A + 16 * c + j] = e * inv; }
+                            const float z = __half2float(*reinterpret_cast<const __half*>(kt + chunk_off(row, q + (j >> 3)) + (j & 7) * 2));
+                            p.P[(size_t)b * A + 16 * c + j] = wn::exp2f_fast(fmaf(z, 1.4426950408889634f, -mxs)) * inv;
                         }
                     }
                 }
