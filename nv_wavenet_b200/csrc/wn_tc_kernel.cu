@@ -153,7 +153,9 @@ template <int S>
 __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const unsigned char* __restrict__ img, const int nstage)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET (not by pointer round-trip through an integer): the compiler keeps knowing these
+    // are shared-memory addresses and emits LDS/STS instead of generic LD/ST
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int L = p.L, B = p.B;
     const TcImage im = tc_image(S, L);
 
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         tmem_ld32(d1 + 32 * hh, ta);
                         tmem_ld32(d1 + 64 + 32 * hh, sa);
                         tmem_ld_wait();
+                        if (tid == 0) TRACE(0, 30 + 2 * hh);
                         uint32_t hp[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
@@ -469,6 +472,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 #pragma unroll
                         for (int q = 0; q < 4; q++)
                             *reinterpret_cast<uint4*>(th + chunk_off(row, 4 * hh + q)) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+                        if (tid == 0) TRACE(0, 31 + 2 * hh);
                     }
                 }
                 if (tid == 0) TRACE(0, 12);
@@ -485,6 +489,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         uint32_t v[32];
                         tmem_ld32(d1 + 32 * hh, v);
                         tmem_ld_wait();
+                        if (tid == 0) TRACE(0, 40 + 2 * hh);
                         uint32_t o[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
@@ -501,6 +506,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                             for (int q = 0; q < 4; q++)
                                 *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 4 * hh + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
                         }
+                        if (tid == 0) TRACE(0, 41 + 2 * hh);
                     }
                     // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
                     // next contribution is only issued after the arrival below: the per-layer dump needs no extra barrier

@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(192, 1) umma_selftest_kernel(const __half* __r
                                                                int N, int K, float* __restrict__ D, int mode)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET (not by pointer round-trip through an integer): the compiler keeps knowing these
+    // are shared-memory addresses and emits LDS/STS instead of generic LD/ST
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int KT = K / 64;
     const int rows_per_chunk = N < 128 ? N : 128;
     const int chunks_n = N / rows_per_chunk;

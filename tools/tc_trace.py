@@ -22,7 +22,8 @@ assert lib.nvwn_debug_trace(e._h, T, None, 0) == 0
 e.run(N, B, None); torch.cuda.synchronize()
 buf = np.zeros(3 * 1024, np.uint64)
 assert lib.nvwn_debug_trace(e._h, T, buf.ctypes.data, 1) == 0
-names = {1: "x0 arrive", 2: "D1 full seen", 12: "E1 math done", 3: "h arrive", 4: "Dx full seen", 5: "x arrive", 6: "skip full seen",
+names = {30: " E1 ld0 done", 31: " E1 half0 done", 32: " E1 ld1 done", 33: " E1 half1 done", 40: " E2 ld0 done", 41: " E2 half0 done",
+         42: " E2 ld1 done", 43: " E2 half1 done", 1: "x0 arrive", 2: "D1 full seen", 12: "E1 math done", 3: "h arrive", 4: "Dx full seen", 5: "x arrive", 6: "skip full seen",
          7: "skq arrive", 9: "zsq arrive", 10: "Dza seen", 11: "sample done", 20: "mma: x seen", 21: "mma: cur issued",
          22: "mma: h seen", 23: "mma: res issued", 24: "mma: layer issued"}
 ev = []
@@ -34,7 +35,8 @@ for role in range(3):
 ev.sort()
 t0 = ev[0][0]
 prev = t0
-for clk, role, tag in ev[:int(sys.argv[2]) if len(sys.argv) > 2 else 70]:
+lo = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+for clk, role, tag in ev[lo:lo + (int(sys.argv[2]) if len(sys.argv) > 2 else 70)]:
     print(f"{clk - t0:8d} (+{clk - prev:6d})  role{role}  {names.get(tag, 'prod layer %d' % (tag - 100) if tag >= 100 else tag)}")
     prev = clk
 print("total cycles in sample:", ev[-1][0] - t0, "events", len(ev))
