@@ -26,7 +26,8 @@ using namespace sm100;
 
 constexpr int R = 64, A = 256;
 constexpr int TILE = 16384;                 // [128 rows x 64 fp16] K-major SW128
-constexpr int NT = 192;
+constexpr int NT = 320;                     // 8 epilogue warps + TMA producer warp + MMA issuer warp
+constexpr int NEPI = 256;
 
 struct TcImage {                            // byte offsets inside the packed image
     size_t layer_bytes, off_out, off_bias, total;
@@ -51,7 +52,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int S, int L, int nstage)
 {
     // 4 activation tiles + ring + 64x64 identity + biases (Bh, Bres, Bskip-sum, Bzs, Bza) + dilations + barriers
     return 1024 + 4 * (size_t)TILE + (size_t)nstage * TILE + TILE / 2 + ((size_t)L * 192 + S + 2 * A) * sizeof(float) + (size_t)L * 4 +
-           (2 * nstage + 8) * 8 + 16;
+           128 * 5 * sizeof(float) + (2 * nstage + 8) * 8 + 16;
 }
 
 // Conditioning in the tensor-core layout: fp16 [N][L][Bpad rows][2 halves of 64 channels], tiled per 128 utterances;
@@ -170,7 +171,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     float* s_bzs = s_bsk + S;
     float* s_bza = s_bzs + A;
     int* s_dil = reinterpret_cast<int*>(s_bza + A);
-    uint64_t* w_full = reinterpret_cast<uint64_t*>(s_dil + L + (L & 1));
+    float* s_pair = reinterpret_cast<float*>(s_dil + L + (L & 1));      // [128 rows][2 halves][max, sum] softmax exchange
+    int* s_y = reinterpret_cast<int*>(s_pair + 128 * 4);                // [128] sampled index per utterance
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(s_y + 128);
     uint64_t* w_empty = w_full + nstage;
     uint64_t* epi_done = w_empty + nstage;
     uint64_t* d1_full = epi_done + 1;
@@ -190,14 +193,14 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 
     if (tid == 0) {
         for (int s = 0; s < nstage; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(epi_done, 128);
+        mbar_init(epi_done, NEPI);
         mbar_init(d1_full, 1); mbar_init(dx_full, 1); mbar_init(skip_full, 1); mbar_init(out_full, 1);
         fence_mbar_init();
         // dilation of layer l (nv_wavenet.cuh:99-111): 1,2,4..maxDil,1,2,...
         int d = 1;
         for (int l = 0; l < L; l++) { s_dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; }
     }
-    if (warp == 4) tmem_alloc<512>(tmem_slot);
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
     {   // biases and the identity tile -> shared memory
         const float* gb = reinterpret_cast<const float*>(img + im.off_bias);
         for (int i = tid; i < L * 128; i += NT) s_bh[i] = gb[im.b_bh + i];
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     int trn = 0;
 #define TRACE(role, tag) do { if (trc && t == p.trace_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
 
-    if (warp == 4) {
+    if (warp == 8) {
         // =============================================================== TMA producer (whole warp converged, one lane issues)
         {
             int stage = 0;
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 for (int c = 0; c < (S / 64) * 2 + (A / 64) * 2; c++) put(ow + (size_t)c * TILE, TILE);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // =============================================================== MMA issuer (whole warp converged, one lane issues)
         {
             const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
@@ -380,30 +383,35 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             }
         }
     } else {
-        // =============================================================== epilogue warps: one thread per utterance
-        const int row = tid;
+        // =============================================================== epilogue: 8 warps, TWO threads per utterance
+        // Warp w works on TMEM lane quadrant w % 4 (hardware rule) and on channel half w / 4: thread (quad, lane, ch)
+        // owns row 32*quad + lane and channels [32 ch, 32 ch + 32) of the 64-wide residual / gate, i.e. 16-byte chunks
+        // 4 ch .. 4 ch + 3 of its row in every 128-byte tile row.  Two warps per scheduler hide each other's latencies.
+        const int quad = warp & 3, ch = warp >> 2;
+        const int row = quad * 32 + lane;
         const int b = tile * 128 + row;
         const bool valid = b < B;
-        const bool wv = tile * 128 + warp * 32 < B;     // warp has at least one live utterance: dead warps only keep the
+        const bool wv = tile * 128 + quad * 32 < B;     // warp has at least one live utterance: dead warps only keep the
                                                         // barrier protocol going (their rows of every tile are never read back)
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const int c32 = 32 * ch, q4 = 4 * ch;
         uint32_t ph_d1 = 0, ph_dx = 0, ph_skip = 0, ph_out = 0;
         const __half* embPrev = static_cast<const __half*>(p.embPrev);
         const __half* embCur = static_cast<const __half*>(p.embCur);
         const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
         int yp = valid ? p.yPrev[b] : 0, yc = valid ? p.yCur[b] : 0;
-        float x[R];                                   // residual stream of this utterance (fp32)
+        float x[32];                                  // this thread's half of the residual stream (fp32)
 #pragma unroll
-        for (int i = 0; i < R; i++) x[i] = 0.f;
+        for (int i = 0; i < 32; i++) x[i] = 0.f;
         // History ring (global, read back d samples later by TMA): written AFTER the barrier arrival that publishes the
         // shared-memory tile, then fenced towards the async proxy while this thread would be waiting for the MMA anyway.
         auto store_history = [&](unsigned char* grow) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < 4; q++) {
                 uint32_t o[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) o[j] = pack_h2(x[8 * q + 2 * j], x[8 * q + 2 * j + 1]);
-                *reinterpret_cast<uint4*>(grow + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(grow + chunk_off(row, q4 + q)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
             fence_proxy_async_global();
         };
@@ -412,16 +420,40 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             fence_proxy_async_smem();
             mbar_arrive(epi_done);
         };
+        auto epi_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        // relu(acc + bias) of this thread's half of a 256(or S)-wide accumulator -> fp16 rows of the 4-k-tile activation tile
+        auto relu_to_tile = [&](uint32_t dacc, const float* bias, int width, float* dump_dst) {
+            const int c_lo = ch * (width / 2);
+#pragma unroll 1
+            for (int c0 = c_lo; c0 < c_lo + width / 2; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(dacc + lane_off + c0, v);
+                tmem_ld_wait();
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float v0 = fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + bias[c0 + j + 1], 0.f);
+                    if (!valid) { v0 = 0.f; v1 = 0.f; }
+                    o[j >> 1] = pack_h2(v0, v1);
+                    if (dump_dst && valid) { dump_dst[c0 + j] = v0; dump_dst[c0 + j + 1] = v1; }
+                }
+                unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
+                const int q = (c0 & 63) >> 3;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q + i)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+        };
 
         for (int t = t_begin; t < t_end; t++) {
             const bool dump = p.dump && (t == t_end - 1);
             const float sel = valid ? __ldg(p.sel + (size_t)t * B + b) : 0.5f;
             // ---------------- embedding: x0 = tanh(embPrev[yPrev] + embCur[yCur])   (reference.cpp:42-57)
             if (wv) {
-                const uint4* ep = reinterpret_cast<const uint4*>(embPrev + (size_t)yp * R);
-                const uint4* ec = reinterpret_cast<const uint4*>(embCur + (size_t)yc * R);
+                const uint4* ep = reinterpret_cast<const uint4*>(embPrev + (size_t)yp * R + c32);
+                const uint4* ec = reinterpret_cast<const uint4*>(embCur + (size_t)yc * R + c32);
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
+                for (int q = 0; q < 4; q++) {
                     const uint4 a = __ldg(ep + q), c = __ldg(ec + q);
                     const uint32_t av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
                     uint32_t o[4];
@@ -434,7 +466,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         x[8 * q + 2 * j] = e0; x[8 * q + 2 * j + 1] = e1;
                         o[j] = pack_h2(e0, e1);
                     }
-                    *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q4 + q)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
             publish();                                                  // x_0 ready
@@ -450,30 +482,24 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 tc_fence_after_sync();
                 if (tid == 0) TRACE(0, 2);
                 if (wv) {
-                    const float* bh = s_bh + (size_t)l * 128;
+                    const float* bh = s_bh + (size_t)l * 128 + c32;
+                    uint32_t ta[32], sa[32];
+                    tmem_ld32(d1 + c32, ta);
+                    tmem_ld32(d1 + 64 + c32, sa);
+                    tmem_ld_wait();
+                    uint32_t hp[16];
 #pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        uint32_t ta[32], sa[32];
-                        tmem_ld32(d1 + 32 * hh, ta);
-                        tmem_ld32(d1 + 64 + 32 * hh, sa);
-                        tmem_ld_wait();
-                        if (tid == 0) TRACE(0, 30 + 2 * hh);
-                        uint32_t hp[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const int r0 = 32 * hh + j;
-                            const float2 bt = *reinterpret_cast<const float2*>(bh + r0), bs = *reinterpret_cast<const float2*>(bh + 64 + r0);
-                            const float a0 = __uint_as_float(ta[j]) + bt.x, a1 = __uint_as_float(ta[j + 1]) + bt.y;
-                            const float g0 = __uint_as_float(sa[j]) + bs.x, g1 = __uint_as_float(sa[j + 1]) + bs.y;
-                            const float h0 = wn::tanhf_fast(a0) * wn::sigmoidf_fast(g0);
-                            const float h1 = wn::tanhf_fast(a1) * wn::sigmoidf_fast(g1);
-                            hp[j >> 1] = pack_h2(h0, h1);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            *reinterpret_cast<uint4*>(th + chunk_off(row, 4 * hh + q)) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
-                        if (tid == 0) TRACE(0, 31 + 2 * hh);
+                    for (int j = 0; j < 32; j += 2) {
+                        const float2 bt = *reinterpret_cast<const float2*>(bh + j), bs = *reinterpret_cast<const float2*>(bh + 64 + j);
+                        const float a0 = __uint_as_float(ta[j]) + bt.x, a1 = __uint_as_float(ta[j + 1]) + bt.y;
+                        const float g0 = __uint_as_float(sa[j]) + bs.x, g1 = __uint_as_float(sa[j + 1]) + bs.y;
+                        const float h0 = wn::tanhf_fast(a0) * wn::sigmoidf_fast(g0);
+                        const float h1 = wn::tanhf_fast(a1) * wn::sigmoidf_fast(g1);
+                        hp[j >> 1] = pack_h2(h0, h1);
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        *reinterpret_cast<uint4*>(th + chunk_off(row, q4 + q)) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
                 }
                 if (tid == 0) TRACE(0, 12);
                 publish();                                              // h ready, D1 drained
@@ -483,41 +509,41 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 tc_fence_after_sync();
                 if (tid == 0) TRACE(0, 4);
                 if (wv) {
-                    const float* br = s_bres + (size_t)l * 64;
+                    const float* br = s_bres + (size_t)l * 64 + c32;
+                    uint32_t v[32];
+                    tmem_ld32(d1 + c32, v);
+                    tmem_ld_wait();
+                    uint32_t o[16];
 #pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        uint32_t v[32];
-                        tmem_ld32(d1 + 32 * hh, v);
-                        tmem_ld_wait();
-                        if (tid == 0) TRACE(0, 40 + 2 * hh);
-                        uint32_t o[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const int r0 = 32 * hh + j;
-                            const float2 bb = *reinterpret_cast<const float2*>(br + r0);
-                            float v0 = x[r0] + (__uint_as_float(v[j]) + bb.x), v1 = x[r0 + 1] + (__uint_as_float(v[j + 1]) + bb.y);
-                            if (!valid) { v0 = 0.f; v1 = 0.f; }
-                            x[r0] = v0; x[r0 + 1] = v1;
-                            o[j >> 1] = pack_h2(v0, v1);
-                            if (dump && valid) { p.xtOut[((size_t)l * B + b) * R + r0] = v0; p.xtOut[((size_t)l * B + b) * R + r0 + 1] = v1; }
-                        }
-                        if (l + 1 < L) {
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                *reinterpret_cast<uint4*>(t_xc + chunk_off(row, 4 * hh + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-                        }
-                        if (tid == 0) TRACE(0, 41 + 2 * hh);
+                    for (int j = 0; j < 32; j += 2) {
+                        const float2 bb = *reinterpret_cast<const float2*>(br + j);
+                        float v0 = x[j] + (__uint_as_float(v[j]) + bb.x), v1 = x[j + 1] + (__uint_as_float(v[j + 1]) + bb.y);
+                        if (!valid) { v0 = 0.f; v1 = 0.f; }
+                        x[j] = v0; x[j + 1] = v1;
+                        o[j >> 1] = pack_h2(v0, v1);
                     }
-                    // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
-                    // next contribution is only issued after the arrival below: the per-layer dump needs no extra barrier
-                    if (dump && l > 0) {
-                        for (int c0 = 0; c0 < S; c0 += 16) {
-                            uint32_t v[16];
-                            tmem_ld16(DSKIP + lane_off + c0, v);
-                            tmem_ld_wait();
-                            if (valid)
-                                for (int j = 0; j < 16; j++)
-                                    p.skipOut[((size_t)(l - 1) * B + b) * S + c0 + j] = __uint_as_float(v[j]) + gbias[im.b_bskp + (size_t)(l - 1) * S + c0 + j];
+                    if (l + 1 < L) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q4 + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    }
+                    if (dump) {                                         // last sample of a dumping launch only
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) p.xtOut[((size_t)l * B + b) * R + c32 + j] = x[j];
+                        }
+                        // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
+                        // next contribution is only issued after the arrival below: no extra barrier needed
+                        if (l > 0) {
+                            const int c_lo = ch * (S / 2);
+                            for (int c0 = c_lo; c0 < c_lo + S / 2; c0 += 16) {
+                                uint32_t w[16];
+                                tmem_ld16(DSKIP + lane_off + c0, w);
+                                tmem_ld_wait();
+                                if (valid)
+                                    for (int j = 0; j < 16; j++)
+                                        p.skipOut[((size_t)(l - 1) * B + b) * S + c0 + j] = __uint_as_float(w[j]) + gbias[im.b_bskp + (size_t)(l - 1) * S + c0 + j];
+                            }
                         }
                     }
                 }
@@ -532,72 +558,44 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             mbar_wait(skip_full, ph_skip); ph_skip ^= 1;
             tc_fence_after_sync();
             if (tid == 0) TRACE(0, 6);
-            if (wv) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < S; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(DSKIP + lane_off + c0, v);
-                    tmem_ld_wait();
-                    uint32_t o[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        float v0 = fmaxf(__uint_as_float(v[j]) + s_bsk[c0 + j], 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + s_bsk[c0 + j + 1], 0.f);
-                        if (!valid) { v0 = 0.f; v1 = 0.f; }
-                        o[j >> 1] = pack_h2(v0, v1);
-                        if (dump && valid) { p.skipOut[((size_t)(L - 1) * B + b) * S + c0 + j] = v0; p.skipOut[((size_t)(L - 1) * B + b) * S + c0 + j + 1] = v1; }
-                    }
-                    unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
-                    const int q = (c0 & 63) >> 3;
-                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
-                }
-            }
+            if (wv) relu_to_tile(DSKIP, s_bsk, S, dump ? p.skipOut + ((size_t)(L - 1) * B + b) * S : nullptr);
             publish();                                                  // relu(skip) tile ready
             if (tid == 0) TRACE(0, 7);
 
             // ---------------- Zs = relu(Wzs . skip + Bzs)   (reference.cpp:96-98)
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
-            if (wv) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < A; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(DZS + lane_off + c0, v);
-                    tmem_ld_wait();
-                    uint32_t o[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        float v0 = fmaxf(__uint_as_float(v[j]) + s_bzs[c0 + j], 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + s_bzs[c0 + j + 1], 0.f);
-                        if (!valid) { v0 = 0.f; v1 = 0.f; }
-                        o[j >> 1] = pack_h2(v0, v1);
-                        if (dump && valid) { p.Zs[(size_t)b * A + c0 + j] = v0; p.Zs[(size_t)b * A + c0 + j + 1] = v1; }
-                    }
-                    unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
-                    const int q = (c0 & 63) >> 3;
-                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
-                }
-            }
+            if (wv) relu_to_tile(DZS, s_bzs, A, dump ? p.Zs + (size_t)b * A : nullptr);
             publish();                                                  // relu(Zs) tile ready
             if (tid == 0) TRACE(0, 9);
 
-            // ---------------- Za, softmax, categorical sample -- all inside this thread   (reference.cpp:100-121)
-            // TMEM -> register bandwidth is the scarce resource: the logits are read from TMEM ONCE, parked as fp16 in this
-            // thread's own row of the (now dead) activation tiles, and the exp / scan passes run from shared memory.
+            // ---------------- Za, softmax, categorical sample   (reference.cpp:100-121)
+            // The two threads of an utterance each take 128 logits: one TMEM pass parks them as fp16 in the thread's own row
+            // of the (now dead) activation tiles and finds the local max; exp / sums / scan run from shared memory; the
+            // halves meet through s_pair (local max, local sum) and s_y.
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
             if (tid == 0) TRACE(0, 10);
-            int y = A - 1;
+            constexpr int HALF = A / 2, NCH = HALF / 16;
+            const int a_lo = ch * HALF;
+            float mx = 0.f;                                             // matrix.cpp:171 starts the max at 0
+            float csum[NCH];
+            float lsum = 0.f;
+            float mxs = 0.f;
+            auto expz = [&](uint32_t packed, float& e0, float& e1) {
+                const float2 z = unpack_h2(packed);
+                e0 = wn::exp2f_fast(fmaf(z.x, 1.4426950408889634f, -mxs));
+                e1 = wn::exp2f_fast(fmaf(z.y, 1.4426950408889634f, -mxs));
+            };
             if (wv) {
-                float mx = 0.f;                                         // matrix.cpp:171 starts the max at 0
 #pragma unroll 1
-                for (int c0 = 0; c0 < A; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(DZA + lane_off + c0, v);
+                for (int c0 = a_lo; c0 < a_lo + HALF; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(DZA + lane_off + c0, v);
                     tmem_ld_wait();
-                    uint32_t o[8];
+                    uint32_t o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
+                    for (int j = 0; j < 32; j += 2) {
                         const float z0 = __uint_as_float(v[j]) + s_bza[c0 + j], z1 = __uint_as_float(v[j + 1]) + s_bza[c0 + j + 1];
                         mx = fmaxf(mx, fmaxf(z0, z1));
                         o[j >> 1] = pack_h2(z0, z1);
@@ -605,74 +603,83 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     }
                     unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
                     const int q = (c0 & 63) >> 3;
-                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
-                }
-                const float mxs = mx * 1.4426950408889634f;
-                auto expz = [&](uint32_t packed, float& e0, float& e1) {
-                    const float2 z = unpack_h2(packed);
-                    e0 = wn::exp2f_fast(fmaf(z.x, 1.4426950408889634f, -mxs));
-                    e1 = wn::exp2f_fast(fmaf(z.y, 1.4426950408889634f, -mxs));
-                };
-                float csum[A / 16];
-                float total = 0.f;
 #pragma unroll
-                for (int c = 0; c < A / 16; c++) {
-                    const unsigned char* kt = t_big + (size_t)(c >> 2) * TILE;
-                    const int q = (c & 3) * 2;
+                    for (int i = 0; i < 4; i++)
+                        *reinterpret_cast<uint4*>(kt + chunk_off(row, q + i)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+                mxs = mx * 1.4426950408889634f;
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    const int c0 = a_lo + 16 * c;
+                    const unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
+                    const int q = (c0 & 63) >> 3;
                     const uint4 u0 = *reinterpret_cast<const uint4*>(kt + chunk_off(row, q)), u1 = *reinterpret_cast<const uint4*>(kt + chunk_off(row, q + 1));
                     const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-                    float s = 0.f;
+                    float sacc = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { float e0, e1; expz(w[j], e0, e1); s += e0; s += e1; }
-                    csum[c] = s;
-                    total += s;
+                    for (int j = 0; j < 8; j++) { float e0, e1; expz(w[j], e0, e1); sacc += e0; sacc += e1; }
+                    csum[c] = sacc;
+                    lsum += sacc;
                 }
+                s_pair[(row * 2 + ch) * 2] = mx;
+                s_pair[(row * 2 + ch) * 2 + 1] = lsum;
+            }
+            epi_bar();
+            int y = A - 1;
+            if (wv) {
+                const float m0 = s_pair[(row * 2) * 2], s0 = s_pair[(row * 2) * 2 + 1], m1 = s_pair[(row * 2 + 1) * 2], s1 = s_pair[(row * 2 + 1) * 2 + 1];
+                const float M = fmaxf(m0, m1);
+                const float f0 = wn::exp2f_fast((m0 - M) * 1.4426950408889634f), f1 = wn::exp2f_fast((m1 - M) * 1.4426950408889634f);
+                const float S0 = s0 * f0, total = S0 + s1 * f1;
                 const float target = sel * total;
-                int cb = A / 16 - 1;
-                float base = 0.f;
-                {
-                    float run = 0.f;
-                    bool found = false;
+                const bool mine = (ch == 0) ? (target < S0) : !(target < S0);
+                const float fme = ch ? f1 : f0, off = ch ? S0 : 0.f;
+                if (mine) {
+                    int cb = NCH - 1;
+                    float base = off;
+                    {
+                        float run = off;
+                        bool found = false;
 #pragma unroll
-                    for (int c = 0; c < A / 16; c++) {
-                        if (!found && target < run + csum[c]) { cb = c; base = run; found = true; }
-                        run += csum[c];
+                        for (int c = 0; c < NCH; c++) {
+                            const float nxt = run + csum[c] * fme;
+                            if (!found && target < nxt) { cb = c; base = run; found = true; }
+                            run = nxt;
+                        }
+                        if (!found) base = run - csum[NCH - 1] * fme;
                     }
-                    if (!found) base = run - csum[A / 16 - 1];
-                }
-                {   // scan inside the chosen 16-logit chunk (own row, own chunk: plain shared-memory reads)
-                    const unsigned char* kt = t_big + (size_t)(cb >> 2) * TILE;
-                    const int q = (cb & 3) * 2;
+                    const int c0 = a_lo + 16 * cb;
+                    const unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
+                    const int q = (c0 & 63) >> 3;
                     const uint4 u0 = *reinterpret_cast<const uint4*>(kt + chunk_off(row, q)), u1 = *reinterpret_cast<const uint4*>(kt + chunk_off(row, q + 1));
                     const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
                     float run = base;
                     bool found = false;
+                    int yy = (cb == NCH - 1 && ch == 1) ? A - 1 : c0 + 15;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         float e0, e1;
                         expz(w[j], e0, e1);
-                        run += e0;
-                        if (!found && target < run) { y = 16 * cb + 2 * j; found = true; }
-                        run += e1;
-                        if (!found && target < run) { y = 16 * cb + 2 * j + 1; found = true; }
+                        run += e0 * fme;
+                        if (!found && target < run) { yy = c0 + 2 * j; found = true; }
+                        run += e1 * fme;
+                        if (!found && target < run) { yy = c0 + 2 * j + 1; found = true; }
                     }
-                    if (!found) y = (cb == A / 16 - 1) ? A - 1 : 16 * cb + 15;
+                    s_y[row] = yy;
+                    if (valid) p.yOut[(size_t)b * p.N + t] = yy;
                 }
                 if (dump && valid) {
-                    const float inv = 1.f / total;
-                    for (int c = 0; c < A / 16; c++) {
-                        const unsigned char* kt = t_big + (size_t)(c >> 2) * TILE;
-                        const int q = (c & 3) * 2;
-                        for (int j = 0; j < 16; j++) {
-                            const float z = __half2float(*reinterpret_cast<const __half*>(kt + chunk_off(row, q + (j >> 3)) + (j & 7) * 2));
-                            p.P[(size_t)b * A + 16 * c + j] = wn::exp2f_fast(fmaf(z, 1.4426950408889634f, -mxs)) * inv;
-                        }
+                    const float inv = fme / total;
+                    for (int a = a_lo; a < a_lo + HALF; a++) {
+                        const unsigned char* kt = t_big + (size_t)(a >> 6) * TILE;
+                        const float z = __half2float(*reinterpret_cast<const __half*>(kt + chunk_off(row, (a & 63) >> 3) + (a & 7) * 2));
+                        p.P[(size_t)b * A + a] = wn::exp2f_fast(fmaf(z, 1.4426950408889634f, -mxs)) * inv;
                     }
                 }
             }
+            epi_bar();
+            if (wv) y = s_y[row];
             if (valid) {
-                p.yOut[(size_t)b * p.N + t] = y;
                 const int fb = p.forced ? p.forced[(size_t)b * p.N + t] : y;
                 yp = yc;
                 yc = fb;
@@ -680,13 +687,13 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             if (tid == 0) TRACE(0, 11);
             // Dza is consumed: the x_0-ready arrival of the next sample (or kernel end) releases it
         }
-        if (valid) { p.yPrev[b] = yp; p.yCur[b] = yc; }
+        if (valid && ch == 0) { p.yPrev[b] = yp; p.yCur[b] = yc; }
         tc_fence_before_sync();
     }
 #undef TRACE
 
     __syncthreads();
-    if (warp == 4) tmem_dealloc<512>(tmem_base);
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
 }
 
 int pick_nstage(int S, int L)
