@@ -150,7 +150,10 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t v)
 // chunk q (16 bytes = 8 fp16) of row `row` inside a SW128 tile
 __device__ __forceinline__ uint32_t chunk_off(int row, int q) { return (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4); }
 
-template <int S>
+// DUP (tiles with <= 64 live utterances, e.g. the 64-per-GPU headline case): every utterance occupies TWO rows (u and u+64)
+// of each activation tile / TMEM accumulator, so that all four TMEM lane quadrants -- and with them all four warp
+// schedulers and their MUFU pipes -- work for it: 4 threads per utterance instead of 2, each on 16 of the 64 channels.
+template <int S, bool DUP>
 __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const unsigned char* __restrict__ img, const int nstage)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -249,13 +252,25 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
             };
+            // activation-side tiles (conditioning, history): `bytes` of rows from row 0; with DUP the same rows again from row 64
+            auto put_act = [&](const void* src, uint32_t bytes) {
+                if (!DUP) { put(src, bytes); return; }
+                mbar_wait(&w_empty[stage], ph);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&w_full[stage], 2 * bytes);
+                    tma_load_1d(ring + (size_t)stage * TILE, src, bytes, &w_full[stage]);
+                    tma_load_1d(ring + (size_t)stage * TILE + TILE / 2, src, bytes, &w_full[stage]);
+                }
+                __syncwarp();
+                if (++stage == nstage) { stage = 0; ph ^= 1; }
+            };
             // Chunk order = consumption order of the MMA issuer (see there):
             //   open(0) | cur(0) open(1) res(0) | cur(1) skip(0) open(2) res(1) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
             // where open(l) = Lh[t][l] (two halves) and, if t >= d_l, the x[t-d_l] history tile + Wprev_l.
             auto put_open = [&](int t, int l, int d) {
-                put(cond_ptr(t, l, 0), c_bytes);
-                put(cond_ptr(t, l, 1), c_bytes);
-                if (t >= d) { put(ring_tile(t - d, l), TILE); put(img + (size_t)l * im.layer_bytes, TILE); }
+                put_act(cond_ptr(t, l, 0), c_bytes);
+                put_act(cond_ptr(t, l, 1), c_bytes);
+                if (t >= d) { put_act(ring_tile(t - d, l), DUP ? TILE / 2 : TILE); put(img + (size_t)l * im.layer_bytes, TILE); }
             };
             auto put_skip = [&](int l) {
                 for (int c = 0; c < S / 128; c++) put(img + (size_t)l * im.layer_bytes + 2 * TILE + TILE / 2 + (size_t)c * TILE, TILE);
@@ -387,31 +402,51 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         // Warp w works on TMEM lane quadrant w % 4 (hardware rule) and on channel half w / 4: thread (quad, lane, ch)
         // owns row 32*quad + lane and channels [32 ch, 32 ch + 32) of the 64-wide residual / gate, i.e. 16-byte chunks
         // 4 ch .. 4 ch + 3 of its row in every 128-byte tile row.  Two warps per scheduler hide each other's latencies.
+        constexpr int NS = DUP ? 4 : 2;                 // threads per utterance
+        constexpr int CW = 64 / NS;                     // residual / gate channels per thread
+        constexpr int CQ = CW / 8;                      // 16-byte chunks per thread in a 128-byte tile row
         const int quad = warp & 3, ch = warp >> 2;
-        const int row = quad * 32 + lane;
-        const int b = tile * 128 + row;
+        const int row = quad * 32 + lane;               // TMEM lane / tile row this thread reads
+        const int u = DUP ? (row & 63) : row;           // utterance of the tile
+        const int sub = DUP ? (ch * 2 + (row >> 6)) : ch;   // which CW-wide slice of the channels is mine
+        const int b = tile * 128 + u;
         const bool valid = b < B;
-        const bool wv = tile * 128 + quad * 32 < B;     // warp has at least one live utterance: dead warps only keep the
-                                                        // barrier protocol going (their rows of every tile are never read back)
+        const bool wv = tile * 128 + (DUP ? (quad & 1) : quad) * 32 < B;   // warp has a live utterance: dead warps only keep
+                                                        // the barrier protocol going (their rows are never read back)
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        const int c32 = 32 * ch, q4 = 4 * ch;
+        const int c32 = CW * sub, q4 = CQ * sub;        // first channel / first chunk of this thread
+        // rows of the activation tiles this thread writes: its own row, and with DUP the twin row of the utterance
+        const int row2 = DUP ? (row ^ 64) : row;
+        auto st_tile = [&](unsigned char* tile_base, int q, uint4 v) {
+            *reinterpret_cast<uint4*>(tile_base + chunk_off(row, q)) = v;
+            if (DUP) *reinterpret_cast<uint4*>(tile_base + chunk_off(row2, q)) = v;
+        };
+        auto tmem_ldc = [&](uint32_t addr, uint32_t (&r)[32]) {       // CW columns into r[0..CW)
+            if (CW == 32) { tmem_ld32(addr, r); }
+            else {
+                uint32_t t16[16];
+                tmem_ld16(addr, t16);
+#pragma unroll
+                for (int i = 0; i < 16; i++) r[i] = t16[i];
+            }
+        };
         uint32_t ph_d1 = 0, ph_dx = 0, ph_skip = 0, ph_out = 0;
         const __half* embPrev = static_cast<const __half*>(p.embPrev);
         const __half* embCur = static_cast<const __half*>(p.embCur);
         const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
         int yp = valid ? p.yPrev[b] : 0, yc = valid ? p.yCur[b] : 0;
-        float x[32];                                  // this thread's half of the residual stream (fp32)
+        float x[CW];                                  // this thread's slice of the residual stream (fp32)
 #pragma unroll
-        for (int i = 0; i < 32; i++) x[i] = 0.f;
+        for (int i = 0; i < CW; i++) x[i] = 0.f;
         // History ring (global, read back d samples later by TMA): written AFTER the barrier arrival that publishes the
         // shared-memory tile, then fenced towards the async proxy while this thread would be waiting for the MMA anyway.
         auto store_history = [&](unsigned char* grow) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < CQ; q++) {
                 uint32_t o[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) o[j] = pack_h2(x[8 * q + 2 * j], x[8 * q + 2 * j + 1]);
-                *reinterpret_cast<uint4*>(grow + chunk_off(row, q4 + q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(grow + chunk_off(u, q4 + q)) = make_uint4(o[0], o[1], o[2], o[3]);   // one copy: row u
             }
             fence_proxy_async_global();
         };
@@ -423,9 +458,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         auto epi_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         // relu(acc + bias) of this thread's half of a 256(or S)-wide accumulator -> fp16 rows of the 4-k-tile activation tile
         auto relu_to_tile = [&](uint32_t dacc, const float* bias, int width, float* dump_dst) {
-            const int c_lo = ch * (width / 2);
+            const int c_lo = sub * (width / NS);
 #pragma unroll 1
-            for (int c0 = c_lo; c0 < c_lo + width / 2; c0 += 32) {
+            for (int c0 = c_lo; c0 < c_lo + width / NS; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(dacc + lane_off + c0, v);
                 tmem_ld_wait();
@@ -440,8 +475,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
                 const int q = (c0 & 63) >> 3;
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                    *reinterpret_cast<uint4*>(kt + chunk_off(row, q + i)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                for (int i = 0; i < 4; i++) st_tile(kt, q + i, make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
             }
         };
 
@@ -453,7 +487,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 const uint4* ep = reinterpret_cast<const uint4*>(embPrev + (size_t)yp * R + c32);
                 const uint4* ec = reinterpret_cast<const uint4*>(embCur + (size_t)yc * R + c32);
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < CQ; q++) {
                     const uint4 a = __ldg(ep + q), c = __ldg(ec + q);
                     const uint32_t av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
                     uint32_t o[4];
@@ -466,7 +500,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         x[8 * q + 2 * j] = e0; x[8 * q + 2 * j + 1] = e1;
                         o[j] = pack_h2(e0, e1);
                     }
-                    *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q4 + q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    st_tile(t_xc, q4 + q, make_uint4(o[0], o[1], o[2], o[3]));
                 }
             }
             publish();                                                  // x_0 ready
@@ -484,12 +518,12 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 if (wv) {
                     const float* bh = s_bh + (size_t)l * 128 + c32;
                     uint32_t ta[32], sa[32];
-                    tmem_ld32(d1 + c32, ta);
-                    tmem_ld32(d1 + 64 + c32, sa);
+                    tmem_ldc(d1 + c32, ta);
+                    tmem_ldc(d1 + 64 + c32, sa);
                     tmem_ld_wait();
-                    uint32_t hp[16];
+                    uint32_t hp[CW / 2];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
+                    for (int j = 0; j < CW; j += 2) {
                         const float2 bt = *reinterpret_cast<const float2*>(bh + j), bs = *reinterpret_cast<const float2*>(bh + 64 + j);
                         const float a0 = __uint_as_float(ta[j]) + bt.x, a1 = __uint_as_float(ta[j + 1]) + bt.y;
                         const float g0 = __uint_as_float(sa[j]) + bs.x, g1 = __uint_as_float(sa[j + 1]) + bs.y;
@@ -498,8 +532,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         hp[j >> 1] = pack_h2(h0, h1);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        *reinterpret_cast<uint4*>(th + chunk_off(row, q4 + q)) = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+                    for (int q = 0; q < CQ; q++) st_tile(th, q4 + q, make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]));
                 }
                 if (tid == 0) TRACE(0, 12);
                 publish();                                              // h ready, D1 drained
@@ -511,11 +544,11 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 if (wv) {
                     const float* br = s_bres + (size_t)l * 64 + c32;
                     uint32_t v[32];
-                    tmem_ld32(d1 + c32, v);
+                    tmem_ldc(d1 + c32, v);
                     tmem_ld_wait();
-                    uint32_t o[16];
+                    uint32_t o[CW / 2];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
+                    for (int j = 0; j < CW; j += 2) {
                         const float2 bb = *reinterpret_cast<const float2*>(br + j);
                         float v0 = x[j] + (__uint_as_float(v[j]) + bb.x), v1 = x[j + 1] + (__uint_as_float(v[j + 1]) + bb.y);
                         if (!valid) { v0 = 0.f; v1 = 0.f; }
@@ -524,19 +557,18 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     }
                     if (l + 1 < L) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            *reinterpret_cast<uint4*>(t_xc + chunk_off(row, q4 + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                        for (int q = 0; q < CQ; q++) st_tile(t_xc, q4 + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
                     }
                     if (dump) {                                         // last sample of a dumping launch only
                         if (valid) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) p.xtOut[((size_t)l * B + b) * R + c32 + j] = x[j];
+                            for (int j = 0; j < CW; j++) p.xtOut[((size_t)l * B + b) * R + c32 + j] = x[j];
                         }
                         // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
                         // next contribution is only issued after the arrival below: no extra barrier needed
                         if (l > 0) {
-                            const int c_lo = ch * (S / 2);
-                            for (int c0 = c_lo; c0 < c_lo + S / 2; c0 += 16) {
+                            const int c_lo = sub * (S / NS);
+                            for (int c0 = c_lo; c0 < c_lo + S / NS; c0 += 16) {
                                 uint32_t w[16];
                                 tmem_ld16(DSKIP + lane_off + c0, w);
                                 tmem_ld_wait();
@@ -576,8 +608,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
             if (tid == 0) TRACE(0, 10);
-            constexpr int HALF = A / 2, NCH = HALF / 16;
-            const int a_lo = ch * HALF;
+            constexpr int PART = A / NS, NCH = PART / 16;               // logits per thread, 16-logit chunks per thread
+            const int a_lo = sub * PART;
             float mx = 0.f;                                             // matrix.cpp:171 starts the max at 0
             float csum[NCH];
             float lsum = 0.f;
@@ -589,7 +621,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             };
             if (wv) {
 #pragma unroll 1
-                for (int c0 = a_lo; c0 < a_lo + HALF; c0 += 32) {
+                for (int c0 = a_lo; c0 < a_lo + PART; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(DZA + lane_off + c0, v);
                     tmem_ld_wait();
@@ -601,7 +633,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         o[j >> 1] = pack_h2(z0, z1);
                         if (dump && valid) { p.Za[(size_t)b * A + c0 + j] = z0; p.Za[(size_t)b * A + c0 + j + 1] = z1; }
                     }
-                    unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
+                    unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;      // scratch: own row only
                     const int q = (c0 & 63) >> 3;
 #pragma unroll
                     for (int i = 0; i < 4; i++)
@@ -621,19 +653,27 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     csum[c] = sacc;
                     lsum += sacc;
                 }
-                s_pair[(row * 2 + ch) * 2] = mx;
-                s_pair[(row * 2 + ch) * 2 + 1] = lsum;
+                s_pair[(u * NS + sub) * 2] = mx;
+                s_pair[(u * NS + sub) * 2 + 1] = lsum;
             }
             epi_bar();
             int y = A - 1;
             if (wv) {
-                const float m0 = s_pair[(row * 2) * 2], s0 = s_pair[(row * 2) * 2 + 1], m1 = s_pair[(row * 2 + 1) * 2], s1 = s_pair[(row * 2 + 1) * 2 + 1];
-                const float M = fmaxf(m0, m1);
-                const float f0 = wn::exp2f_fast((m0 - M) * 1.4426950408889634f), f1 = wn::exp2f_fast((m1 - M) * 1.4426950408889634f);
-                const float S0 = s0 * f0, total = S0 + s1 * f1;
+                float pm[NS], ps[NS];
+                float M = 0.f;
+#pragma unroll
+                for (int i = 0; i < NS; i++) { pm[i] = s_pair[(u * NS + i) * 2]; ps[i] = s_pair[(u * NS + i) * 2 + 1]; M = fmaxf(M, pm[i]); }
+                float total = 0.f, off = 0.f, fme = 1.f, mine_hi = 0.f;
+#pragma unroll
+                for (int i = 0; i < NS; i++) {
+                    const float f = wn::exp2f_fast((pm[i] - M) * 1.4426950408889634f);
+                    if (i == sub) { off = total; fme = f; }
+                    total += ps[i] * f;
+                    if (i == sub) mine_hi = total;
+                }
                 const float target = sel * total;
-                const bool mine = (ch == 0) ? (target < S0) : !(target < S0);
-                const float fme = ch ? f1 : f0, off = ch ? S0 : 0.f;
+                // owner = first part whose scaled running sum exceeds the target; the last part takes what is left
+                const bool mine = (sub == 0 || !(target < off)) && (target < mine_hi || sub == NS - 1);
                 if (mine) {
                     int cb = NCH - 1;
                     float base = off;
@@ -655,7 +695,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
                     float run = base;
                     bool found = false;
-                    int yy = (cb == NCH - 1 && ch == 1) ? A - 1 : c0 + 15;
+                    int yy = (cb == NCH - 1 && sub == NS - 1) ? A - 1 : c0 + 15;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         float e0, e1;
@@ -665,12 +705,12 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         run += e1 * fme;
                         if (!found && target < run) { yy = c0 + 2 * j + 1; found = true; }
                     }
-                    s_y[row] = yy;
+                    s_y[u] = yy;
                     if (valid) p.yOut[(size_t)b * p.N + t] = yy;
                 }
                 if (dump && valid) {
                     const float inv = fme / total;
-                    for (int a = a_lo; a < a_lo + HALF; a++) {
+                    for (int a = a_lo; a < a_lo + PART; a++) {
                         const unsigned char* kt = t_big + (size_t)(a >> 6) * TILE;
                         const float z = __half2float(*reinterpret_cast<const __half*>(kt + chunk_off(row, (a & 63) >> 3) + (a & 7) * 2));
                         p.P[(size_t)b * A + a] = wn::exp2f_fast(fmaf(z, 1.4426950408889634f, -mxs)) * inv;
@@ -678,7 +718,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 }
             }
             epi_bar();
-            if (wv) y = s_y[row];
+            if (wv) y = s_y[u];
             if (valid) {
                 const int fb = p.forced ? p.forced[(size_t)b * p.N + t] : y;
                 yp = yc;
@@ -687,7 +727,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             if (tid == 0) TRACE(0, 11);
             // Dza is consumed: the x_0-ready arrival of the next sample (or kernel end) releases it
         }
-        if (valid && ch == 0) { p.yPrev[b] = yp; p.yCur[b] = yc; }
+        if (valid && sub == 0) { p.yPrev[b] = yp; p.yCur[b] = yc; }
         tc_fence_before_sync();
     }
 #undef TRACE
@@ -741,16 +781,18 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t 
     if (nstage < 3) return cudaErrorInvalidValue;
     const size_t smem = tc_smem_bytes(p.S, p.L, nstage);
     const int grid = (p.B + 127) / 128;
-    cudaError_t e;
-    if (p.S == 256) {
-        e = cudaFuncSetAttribute(wn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        wn_tc_kernel<256><<<grid, NT, smem, stream>>>(p, static_cast<const unsigned char*>(tc_image_), nstage);
-    } else {
-        e = cudaFuncSetAttribute(wn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        wn_tc_kernel<128><<<grid, NT, smem, stream>>>(p, static_cast<const unsigned char*>(tc_image_), nstage);
-    }
-    if (info) { info->kernel = 17; info->grid = grid; info->block = NT; info->smem_bytes = (int)smem; info->batch_per_cta = 128; info->cluster = 1; }
+    cudaError_t e = cudaErrorInvalidValue;
+    const bool dup = p.B <= 64 && !getenv("NVWN_TC_NODUP");    // single tile with at most 64 utterances: 4 threads per utterance
+    const unsigned char* im8 = static_cast<const unsigned char*>(tc_image_);
+#define WN_TC_LAUNCH(SV, DV)                                                                                         \
+    do {                                                                                                             \
+        e = cudaFuncSetAttribute(wn_tc_kernel<SV, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        if (e != cudaSuccess) return e;                                                                              \
+        wn_tc_kernel<SV, DV><<<grid, NT, smem, stream>>>(p, im8, nstage);                                           \
+    } while (0)
+    if (p.S == 256) { if (dup) WN_TC_LAUNCH(256, true); else WN_TC_LAUNCH(256, false); }
+    else { if (dup) WN_TC_LAUNCH(128, true); else WN_TC_LAUNCH(128, false); }
+#undef WN_TC_LAUNCH
+    if (info) { info->kernel = 17; info->grid = grid; info->block = NT; info->smem_bytes = (int)smem; info->batch_per_cta = dup ? 64 : 128; info->cluster = 1; }
     return cudaGetLastError();
 }

@@ -159,16 +159,24 @@ def _logit_check(za_o, za_g, rel=1e-2, mean_rel=None):
         assert (err / scale).mean() <= mean_rel, f"mean err / scale {(err / scale).mean()}"
 
 
-@pytest.mark.parametrize("kernel", ["stream", "auto"])
+@pytest.mark.parametrize("kernel", ["stream", "auto", "tc_nodup"])
 @pytest.mark.parametrize("shape", [
     (64, 256, 256, 20, 8, 24, 8),
     (64, 128, 256, 20, 4, 16, 4),
     (64, 256, 256, 20, 64, 12, 4),
+    (64, 256, 256, 20, 130, 6, 2),        # two batch tiles, the second one nearly empty
+    (64, 256, 256, 5, 100, 10, 16),       # odd layer count, partially filled tile
 ])
 def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
     R, S, A, L, B, N, md = shape
     if kernel == "stream":
+        if B > 64:
+            pytest.skip("covered by the smaller shapes")
         monkeypatch.setenv("NVWN_FP16_KERNEL", "stream")
+    if kernel == "tc_nodup":
+        if B > 64:
+            pytest.skip("already the two-thread-per-utterance variant")
+        monkeypatch.setenv("NVWN_TC_NODUP", "1")
     w = refgen.lively_inputs(21 + B, R, S, A, L, B, N)
     # moderate the scales a little so that fp16 GEMM inputs stay well inside range
     o32 = cpu_oracle(w, L, B, N, R, S, A, md)
