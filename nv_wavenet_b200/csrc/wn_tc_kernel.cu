@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
             };
             // Chunk order = consumption order of the MMA issuer (see there):
-            //   open(0) | cur(0) res(0) open(1) | cur(1) skip(0) res(1) open(2) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
+            //   open(0) | cur(0) open(1) res(0) | cur(1) skip(0) open(2) res(1) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
             // where open(l) = Lh[t][l] (two halves) and, if t >= d_l, the x[t-d_l] history tile + Wprev_l.
             auto put_open = [&](int t, int l, int d) {
                 put_act(cond_ptr(t, l, 0), c_bytes);
@@ -284,8 +284,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     if (lane == 0) TRACE(2, 100 + l);
                     put(lw + TILE, TILE);                               // Wcur_l
                     if (l > 0) put_skip(l - 1);
-                    put(lw + 2 * TILE, TILE / 2);                       // Wres_l
                     if (l + 1 < L) put_open(t, l + 1, dn);
+                    put(lw + 2 * TILE, TILE / 2);                       // Wres_l
                     d = dn;
                 }
                 put_skip(L - 1);
@@ -348,9 +348,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     advance();
                 }
             };
-            // Issue order per layer: cur(l) | skip(l-1) in the shadow of the gate epilogue | res(l) | open(l+1) in the shadow
-            // of the residual epilogue.  Nothing but cur / res sits between an epilogue arrival and the accumulator it
-            // waits for, and the background GEMMs fill the tensor pipe while the epilogue warps work.
+            // Issue order per layer: cur(l) | skip(l-1), open(l+1) in the shadow of the gate epilogue | res(l).
+            // The residual epilogue therefore runs with the tensor pipe idle, and nothing but cur / res sits between
+            // an epilogue arrival and the accumulator it waits for.
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
                 for (int l = 0; l < L; l++) {
@@ -365,15 +365,15 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     mma4(d_xc, dw, d1, idesc128, true, d1_full, &w_empty[stage]);       // D1 += Wcur . x[t]
                     advance();
                     if (lane == 0) TRACE(1, 21);
-                    if (l > 0) skip_layer(l - 1, nullptr);              // in the shadow of the gate epilogue
+                    if (l > 0) skip_layer(l - 1, nullptr);
+                    if (l + 1 < L) open_layer(l + 1, t >= dn);
+                    if (lane == 0) TRACE(1, 24);
                     dw = wait_stage();                                  // Wres_l
                     wait_epi();                                         // h tile ready, D1 consumed
                     if (lane == 0) TRACE(1, 22);
                     mma4(d_h + (uint64_t)(l & 1) * TILE_D, dw, d1, idesc64, false, dx_full, &w_empty[stage]);   // Dx = Wres . h
                     advance();
                     if (lane == 0) TRACE(1, 23);
-                    if (l + 1 < L) open_layer(l + 1, t >= dn);          // in the shadow of the residual epilogue
-                    if (lane == 0) TRACE(1, 24);
                     d = dn;
                 }
                 skip_layer(L - 1, skip_full);
