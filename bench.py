@@ -321,7 +321,7 @@ def run_ours(args, rank, world, local_rank):
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get("dram_bytes_per_unit") * B * N      # ncu dram read+write bytes, scaled to this launch
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
