@@ -50,9 +50,9 @@ __host__ __device__ inline TcImage tc_image(int S, int L)
 
 __host__ __device__ inline size_t tc_smem_bytes(int S, int L, int nstage)
 {
-    // 4 activation tiles + ring + 64x64 identity + biases (Bh, Bres, Bskip-sum, Bzs, Bza) + dilations + barriers
-    return 1024 + 4 * (size_t)TILE + (size_t)nstage * TILE + TILE / 2 + ((size_t)L * 192 + S + 2 * A) * sizeof(float) + (size_t)L * 4 +
-           128 * 5 * sizeof(float) + (2 * nstage + 8) * 8 + 16;
+    // 4 activation tiles + weight ring + conditioning buffers (2 tiles) + biases (Bh, Bres, Bskip-sum, Bzs, Bza) + dilations + barriers
+    return 1024 + 4 * (size_t)TILE + (size_t)nstage * TILE + 2 * TILE + ((size_t)L * 192 + S + 2 * A) * sizeof(float) + (size_t)L * 4 +
+           128 * 5 * sizeof(float) + (2 * nstage + 16) * 8 + 16;
 }
 
 // Conditioning in the tensor-core layout: fp16 [N][L][Bpad rows][2 halves of 64 channels], tiled per 128 utterances;
@@ -167,8 +167,12 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     unsigned char* t_h = smem + TILE;              // gated activation tiles, double buffered by layer parity (= BIG k-tiles 1, 2)
     unsigned char* t_big = smem;                   // [128 x 256] as 4 k-tiles: relu(skip), relu(Zs), then fp16 logits scratch
     unsigned char* ring = smem + 4 * TILE;
-    unsigned char* t_ident = ring + (size_t)nstage * TILE;     // 64 x 64 identity (B operand that injects Lh)
-    float* s_bh = reinterpret_cast<float*>(t_ident + TILE / 2);
+    // conditioning buffers: one Lh[t][l] tile = [2 halves][rows][128 B]; DUP tiles (<= 64 rows, 16 KB) are double
+    // buffered, full tiles (32 KB) single buffered
+    unsigned char* t_cond = ring + (size_t)nstage * TILE;
+    constexpr int NC = DUP ? 2 : 1;
+    constexpr int CB = DUP ? TILE : 2 * TILE;
+    float* s_bh = reinterpret_cast<float*>(t_cond + 2 * TILE);
     float* s_bres = s_bh + (size_t)L * 128;
     float* s_bsk = s_bres + (size_t)L * 64;
     float* s_bzs = s_bsk + S;
@@ -183,7 +187,10 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     uint64_t* dx_full = epi_done + 2;
     uint64_t* skip_full = epi_done + 3;
     uint64_t* out_full = epi_done + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 6);
+    uint64_t* pre_done = epi_done + 5;          // accumulator of the coming layer initialised with Lh + bias
+    uint64_t* cond_full = epi_done + 6;         // [NC]
+    uint64_t* cond_empty = epi_done + 8;        // [NC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 12);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, ntiles = gridDim.x;
@@ -198,6 +205,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         for (int s = 0; s < nstage; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         mbar_init(epi_done, NEPI);
         mbar_init(d1_full, 1); mbar_init(dx_full, 1); mbar_init(skip_full, 1); mbar_init(out_full, 1);
+        mbar_init(pre_done, NEPI);
+        for (int i = 0; i < NC; i++) { mbar_init(&cond_full[i], 1); mbar_init(&cond_empty[i], NEPI); }
         fence_mbar_init();
         // dilation of layer l (nv_wavenet.cuh:99-111): 1,2,4..maxDil,1,2,...
         int d = 1;
@@ -210,11 +219,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         for (int i = tid; i < L * 64; i += NT) s_bres[i] = gb[im.b_bres + i];
         for (int i = tid; i < S; i += NT) s_bsk[i] = gb[im.b_bskp + (size_t)(L - 1) * S + i];
         for (int i = tid; i < A; i += NT) { s_bzs[i] = gb[im.b_bzs + i]; s_bza[i] = gb[im.b_bza + i]; }
-        for (int i = tid; i < TILE / 2 / 4; i += NT) reinterpret_cast<uint32_t*>(t_ident)[i] = 0u;
     }
-    __syncthreads();
-    if (tid < 64) *reinterpret_cast<__half*>(t_ident + sw128_offset(tid, tid)) = __float2half_rn(1.0f);
-    fence_proxy_async();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
             };
-            // activation-side tiles (conditioning, history): `bytes` of rows from row 0; with DUP the same rows again from row 64
+            // history tile: `bytes` of rows from row 0; with DUP the same rows again from row 64
             auto put_act = [&](const void* src, uint32_t bytes) {
                 if (!DUP) { put(src, bytes); return; }
                 mbar_wait(&w_empty[stage], ph);
@@ -264,12 +269,25 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
             };
-            // Chunk order = consumption order of the MMA issuer (see there):
-            //   open(0) | cur(0) open(1) res(0) | cur(1) skip(0) open(2) res(1) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
-            // where open(l) = Lh[t][l] (two halves) and, if t >= d_l, the x[t-d_l] history tile + Wprev_l.
-            auto put_open = [&](int t, int l, int d) {
-                put_act(cond_ptr(t, l, 0), c_bytes);
-                put_act(cond_ptr(t, l, 1), c_bytes);
+            // conditioning tile g (g counts layers since the start of the launch) -> buffer g % NC
+            int g_cond = 0;
+            auto put_cond = [&](int t, int l) {
+                const int cbuf = g_cond % NC;
+                mbar_wait(&cond_empty[cbuf], ((g_cond / NC) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&cond_full[cbuf], 2 * c_bytes);
+                    tma_load_1d(t_cond + (size_t)cbuf * CB, cond_ptr(t, l, 0), 2 * c_bytes, &cond_full[cbuf]);   // both halves are contiguous
+                    // pull the tiles a few layers ahead from HBM into L2
+                    int tl = t * L + l + 4;
+                    if (tl < t_end * L) tma_prefetch_l2(cond_ptr(tl / L, tl % L, 0), 2 * c_bytes);
+                }
+                __syncwarp();
+                g_cond++;
+            };
+            // Weight-ring chunk order = consumption order of the MMA issuer (see there):
+            //   prev(0) | cur(0) res(0) prev(1) | cur(1) skip(0) res(1) prev(2) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
+            // where prev(l) = the x[t-d_l] history tile + Wprev_l, present only if t >= d_l.
+            auto put_prev = [&](int t, int l, int d) {
                 if (t >= d) { put_act(ring_tile(t - d, l), DUP ? TILE / 2 : TILE); put(img + (size_t)l * im.layer_bytes, TILE); }
             };
             auto put_skip = [&](int l) {
@@ -277,15 +295,17 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             };
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;
-                put_open(t, 0, 1);
+                put_cond(t, 0);
+                put_prev(t, 0, 1);
                 for (int l = 0; l < L; l++) {
                     const unsigned char* lw = img + (size_t)l * im.layer_bytes;
                     int dn = d << 1; if (dn > p.maxDil) dn = 1;
                     if (lane == 0) TRACE(2, 100 + l);
+                    if (l + 1 < L) put_cond(t, l + 1);
                     put(lw + TILE, TILE);                               // Wcur_l
                     if (l > 0) put_skip(l - 1);
-                    if (l + 1 < L) put_open(t, l + 1, dn);
                     put(lw + 2 * TILE, TILE / 2);                       // Wres_l
+                    if (l + 1 < L) put_prev(t, l + 1, dn);
                     d = dn;
                 }
                 put_skip(L - 1);
@@ -300,8 +320,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             int stage = 0;
             uint32_t ph_full = 0, ph_epi = 0;
             const uint64_t d_ring = make_desc_kmajor_sw128(smem_u32(ring)), d_xc = make_desc_kmajor_sw128(smem_u32(t_xc)),
-                           d_h = make_desc_kmajor_sw128(smem_u32(t_h)), d_big = make_desc_kmajor_sw128(smem_u32(t_big)),
-                           d_ident = make_desc_kmajor_sw128(smem_u32(t_ident));
+                           d_h = make_desc_kmajor_sw128(smem_u32(t_h)), d_big = make_desc_kmajor_sw128(smem_u32(t_big));
+            uint32_t ph_pre = 0;
             constexpr uint64_t TILE_D = TILE >> 4;                      // one tile further, in descriptor address units
             auto wait_stage = [&]() -> uint64_t {                       // descriptor of the next ring stage once its data landed
                 mbar_wait(&w_full[stage], ph_full);
@@ -319,15 +339,11 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
             };
             auto wait_epi = [&]() { mbar_wait(epi_done, ph_epi); ph_epi ^= 1; tc_fence_after_sync(); };
-            // open(l): D1[l&1] = Lh[t][l] (through the identity), then += Wprev_l . x[t-d]; all operands come from the ring
+            // open(l): the epilogue has initialised D1[l&1] with Lh[t][l] + Bh (tcgen05.st); add Wprev_l . x[t-d]
             auto open_layer = [&](int l, bool has_prev) {
                 const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128;
-                for (int half = 0; half < 2; half++) {
-                    const uint64_t da = wait_stage();
-                    tc_fence_after_sync();
-                    mma4(da, d_ident, d1 + 64 * half, idesc64, false, &w_empty[stage], nullptr);
-                    advance();
-                }
+                mbar_wait(pre_done, ph_pre); ph_pre ^= 1;
+                tc_fence_after_sync();
                 if (has_prev) {
                     const uint64_t da = wait_stage();
                     const int sa = stage;
@@ -348,9 +364,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     advance();
                 }
             };
-            // Issue order per layer: cur(l) | skip(l-1), open(l+1) in the shadow of the gate epilogue | res(l).
-            // The residual epilogue therefore runs with the tensor pipe idle, and nothing but cur / res sits between
-            // an epilogue arrival and the accumulator it waits for.
+            // Issue order per layer: cur(l) | skip(l-1) in the shadow of the gate epilogue | res(l) | prev(l+1) in the shadow
+            // of the residual epilogue.  Nothing but cur / res sits between an epilogue arrival and the accumulator it
+            // waits for.
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
                 for (int l = 0; l < L; l++) {
@@ -365,15 +381,15 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     mma4(d_xc, dw, d1, idesc128, true, d1_full, &w_empty[stage]);       // D1 += Wcur . x[t]
                     advance();
                     if (lane == 0) TRACE(1, 21);
-                    if (l > 0) skip_layer(l - 1, nullptr);
-                    if (l + 1 < L) open_layer(l + 1, t >= dn);
-                    if (lane == 0) TRACE(1, 24);
+                    if (l > 0) skip_layer(l - 1, nullptr);              // in the shadow of the gate epilogue
                     dw = wait_stage();                                  // Wres_l
                     wait_epi();                                         // h tile ready, D1 consumed
                     if (lane == 0) TRACE(1, 22);
                     mma4(d_h + (uint64_t)(l & 1) * TILE_D, dw, d1, idesc64, false, dx_full, &w_empty[stage]);   // Dx = Wres . h
                     advance();
                     if (lane == 0) TRACE(1, 23);
+                    if (l + 1 < L) open_layer(l + 1, t >= dn);          // in the shadow of the residual epilogue
+                    if (lane == 0) TRACE(1, 24);
                     d = dn;
                 }
                 skip_layer(L - 1, skip_full);
@@ -456,6 +472,40 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             mbar_arrive(epi_done);
         };
         auto epi_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        // Initialise the pre-activation accumulator of layer `ln` with Lh[tn][ln] + Bh (fp32) straight from the TMA-fed
+        // conditioning buffer: tcgen05.st, done while this thread would otherwise wait for the residual GEMM.  Each row
+        // needs all 128 columns from the two threads that may touch its TMEM lane: channel half `ch`, both gate halves.
+        int g_pre = 0;
+        auto prestore = [&](int ln) {
+            const int cbuf = g_pre % NC;
+            mbar_wait(&cond_full[cbuf], (g_pre / NC) & 1);
+            if (wv) {
+                const unsigned char* cb = t_cond + (size_t)cbuf * CB;
+                const uint32_t d1n = D1B + (uint32_t)(ln & 1) * 128 + lane_off;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const float* bh = s_bh + (size_t)ln * 128 + 64 * half + 32 * ch;
+                    uint32_t v[32];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(cb + (size_t)half * c_bytes + chunk_off(u, 4 * ch + q));
+                        const uint32_t wv4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float2 f = unpack_h2(wv4[j]);
+                            v[8 * q + 2 * j] = __float_as_uint(f.x + bh[8 * q + 2 * j]);
+                            v[8 * q + 2 * j + 1] = __float_as_uint(f.y + bh[8 * q + 2 * j + 1]);
+                        }
+                    }
+                    tmem_st32(d1n + 64 * half + 32 * ch, v);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&cond_empty[cbuf]);
+            mbar_arrive(pre_done);
+            g_pre++;
+        };
         // relu(acc + bias) of this thread's half of a 256(or S)-wide accumulator -> fp16 rows of the 4-k-tile activation tile
         auto relu_to_tile = [&](uint32_t dacc, const float* bias, int width, float* dump_dst) {
             const int c_lo = sub * (width / NS);
@@ -482,6 +532,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         for (int t = t_begin; t < t_end; t++) {
             const bool dump = p.dump && (t == t_end - 1);
             const float sel = valid ? __ldg(p.sel + (size_t)t * B + b) : 0.5f;
+            prestore(0);                                                // D1[0] <- Lh[t][0] + Bh (Dza of the previous sample is consumed)
             // ---------------- embedding: x0 = tanh(embPrev[yPrev] + embCur[yCur])   (reference.cpp:42-57)
             if (wv) {
                 const uint4* ep = reinterpret_cast<const uint4*>(embPrev + (size_t)yp * R + c32);
@@ -510,13 +561,12 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             for (int l = 0; l < L; l++) {
                 const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128 + lane_off;
                 unsigned char* th = t_h + (size_t)(l & 1) * TILE;
-                // ---------------- gate: h = tanh(a[0:R]) * sigmoid(a[R:2R]),  a = D1 + Bh  (D1 already holds
-                // Wprev.x[t-d] + Wcur.x[t] + Lh[t][l])   (reference.cpp:67-80)
+                // ---------------- gate: h = tanh(a[0:R]) * sigmoid(a[R:2R]); D1 already holds the complete pre-activation
+                // a = (Lh[t][l] + Bh) + Wprev.x[t-d] + Wcur.x[t]   (reference.cpp:67-80)
                 mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
                 tc_fence_after_sync();
                 if (tid == 0) TRACE(0, 2);
                 if (wv) {
-                    const float* bh = s_bh + (size_t)l * 128 + c32;
                     uint32_t ta[32], sa[32];
                     tmem_ldc(d1 + c32, ta);
                     tmem_ldc(d1 + 64 + c32, sa);
@@ -524,9 +574,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     uint32_t hp[CW / 2];
 #pragma unroll
                     for (int j = 0; j < CW; j += 2) {
-                        const float2 bt = *reinterpret_cast<const float2*>(bh + j), bs = *reinterpret_cast<const float2*>(bh + 64 + j);
-                        const float a0 = __uint_as_float(ta[j]) + bt.x, a1 = __uint_as_float(ta[j + 1]) + bt.y;
-                        const float g0 = __uint_as_float(sa[j]) + bs.x, g1 = __uint_as_float(sa[j + 1]) + bs.y;
+                        const float a0 = __uint_as_float(ta[j]), a1 = __uint_as_float(ta[j + 1]);
+                        const float g0 = __uint_as_float(sa[j]), g1 = __uint_as_float(sa[j + 1]);
                         const float h0 = wn::tanhf_fast(a0) * wn::sigmoidf_fast(g0);
                         const float h1 = wn::tanhf_fast(a1) * wn::sigmoidf_fast(g1);
                         hp[j >> 1] = pack_h2(h0, h1);
@@ -537,6 +586,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 if (tid == 0) TRACE(0, 12);
                 publish();                                              // h ready, D1 drained
                 if (tid == 0) TRACE(0, 3);
+                if (l + 1 < L) prestore(l + 1);                         // while the residual GEMM runs
                 // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
                 mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
                 tc_fence_after_sync();
