@@ -328,10 +328,19 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             constexpr uint64_t TILE_D = TILE >> 4;                      // one tile further, in descriptor address units
             const uint32_t idesc256 = make_idesc_f16(128, 256);
             // chunk number c lives in stage c % nstage; its full-barrier completes with parity (c / nstage) & 1
-            auto stage_of = [&](uint32_t c) -> int { return (int)(c % (uint32_t)nstage); };
+            // (nstage is 6 for every supported model size; the constant lets the compiler strength-reduce % and /)
+            auto stage_of = [&](uint32_t c) -> int { return nstage == 6 ? (int)(c % 6u) : (int)(c % (uint32_t)nstage); };
+            auto par_of = [&](uint32_t c) -> uint32_t { return (nstage == 6 ? (c / 6u) : (c / (uint32_t)nstage)) & 1u; };
             auto wait_chunk = [&](uint32_t c) -> uint64_t {
                 const int st = stage_of(c);
-                mbar_wait(&w_full[st], (c / (uint32_t)nstage) & 1u);
+                mbar_wait(&w_full[st], par_of(c));
+                return d_ring + (uint64_t)st * TILE_D;
+            };
+            // both chunks of an adjacent pair at once: even lanes poll the first barrier, odd lanes the second
+            auto wait_pair = [&](uint32_t c) -> uint64_t {
+                const int st = stage_of(c);                              // pairs start on even stages: c+1 is st+1, same parity
+                mbar_wait(&w_full[st + (lane & 1)], par_of(c));
+                __syncwarp();
                 return d_ring + (uint64_t)st * TILE_D;
             };
             // 4 K-slices of one 64-deep chunk, then up to three commits; single elected lane
@@ -352,18 +361,17 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 mbar_wait(pre_done, ph_pre); ph_pre ^= 1;
                 tc_fence_after_sync();
                 if (has_prev) {
-                    const uint64_t da = wait_chunk(c), db = wait_chunk(c + 1);
+                    const uint64_t da = wait_pair(c), db = da + TILE_D;
                     tc_fence_after_sync();
-                    mma4(da, db, d1, idesc128, true, &w_empty[stage_of(c)], &w_empty[stage_of(c + 1)], nullptr);
+                    mma4(da, db, d1, idesc128, true, &w_empty[stage_of(c)], &w_empty[stage_of(c) + 1], nullptr);
                 }
             };
             // skip(l): Dskip (+)= Wskip_l . h_l as ONE N=S instruction per K slice (chunks c, c+1 are adjacent in smem)
             auto skip_layer = [&](int l, uint32_t c, uint64_t* done_bar) {
                 const uint64_t dh = d_h + (uint64_t)(l & 1) * TILE_D;
-                const uint64_t dw = wait_chunk(c);
-                wait_chunk(c + 1);
+                const uint64_t dw = wait_pair(c);
                 tc_fence_after_sync();
-                mma4(dh, dw, DSKIP, S == 256 ? idesc256 : idesc128, l > 0, &w_empty[stage_of(c)], &w_empty[stage_of(c + 1)], done_bar);
+                mma4(dh, dw, DSKIP, S == 256 ? idesc256 : idesc128, l > 0, &w_empty[stage_of(c)], &w_empty[stage_of(c) + 1], done_bar);
             };
             // Issue order per layer: cur(l) | skip(l-1) in the shadow of the gate epilogue | res(l) | prev(l+1) in the shadow
             // of the residual epilogue.  Nothing but cur / res sits between an epilogue arrival and the accumulator it
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     const bool hpn = (l + 1 < L) && (t >= dn);
                     const uint32_t c_prev_next = cc + 2 + (l > 0 ? 2 : 0);
                     cc = c_prev_next + (hpn ? 2 : 0);
-                    const uint64_t dwc = wait_chunk(c_cur);             // Wcur_l is in flight long before x_l
+                    const uint64_t dwc = wait_pair(c_cur);              // Wcur_l and Wres_l (a pair) are in flight long before x_l
                     wait_epi();                                         // x_l tile ready (and, for l = 0, Dza consumed)
                     if (lane == 0) TRACE(1, 20);
                     if (l == 0) open_layer(0, hp0, cprev);
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     mma4(d_xc, dwc, d1, idesc128, true, d1_full, &w_empty[stage_of(c_cur)], nullptr);       // D1 += Wcur . x[t]
                     if (lane == 0) TRACE(1, 21);
                     if (l > 0) skip_layer(l - 1, c_skip, nullptr);      // in the shadow of the gate epilogue
-                    const uint64_t dwr = wait_chunk(c_res);             // Wres_l
+                    const uint64_t dwr = dwc + TILE_D;                  // Wres_l: second chunk of the pair
                     wait_epi();                                         // h tile ready, D1 consumed
                     if (lane == 0) TRACE(1, 22);
                     mma4(d_h + (uint64_t)(l & 1) * TILE_D, dwr, d1, idesc64, false, dx_full, &w_empty[stage_of(c_res)], nullptr);   // Dx = Wres . h
@@ -401,19 +409,17 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 cc += 2;
                 wait_epi();                                             // relu(skip) tile ready
                 for (int kt = 0; kt < S / 64; kt++) {                   // Zs: one N=256 instruction per K slice
-                    const uint64_t dw = wait_chunk(cc);
-                    wait_chunk(cc + 1);
+                    const uint64_t dw = wait_pair(cc);
                     tc_fence_after_sync();
-                    mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS, idesc256, kt > 0, &w_empty[stage_of(cc)], &w_empty[stage_of(cc + 1)],
+                    mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS, idesc256, kt > 0, &w_empty[stage_of(cc)], &w_empty[stage_of(cc) + 1],
                          kt == S / 64 - 1 ? out_full : nullptr);
                     cc += 2;
                 }
                 wait_epi();                                             // relu(Zs) tile ready
                 for (int kt = 0; kt < A / 64; kt++) {
-                    const uint64_t dw = wait_chunk(cc);
-                    wait_chunk(cc + 1);
+                    const uint64_t dw = wait_pair(cc);
                     tc_fence_after_sync();
-                    mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA, idesc256, kt > 0, &w_empty[stage_of(cc)], &w_empty[stage_of(cc + 1)],
+                    mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA, idesc256, kt > 0, &w_empty[stage_of(cc)], &w_empty[stage_of(cc) + 1],
                          kt == A / 64 - 1 ? out_full : nullptr);
                     cc += 2;
                 }
