@@ -284,17 +284,14 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
                 g_cond++;
             };
-            // Weight-ring chunk order (the issuer addresses stages by chunk counter, not by arrival order):
-            //   [prev(0)] | cur(0) res(0) . . [prev(1)] | cur(1) res(1) skip(0)a skip(0)b [prev(2)] | ... | skip(L-1) | Wzs | Wza
-            // Every group is an even number of 16 KB chunks and the ring has an even number of stages, so the two chunks of
-            // a skip / output-layer pair are always adjacent in shared memory: one N=256 MMA per K slice reads both.
-            // prev(l) = the x[t-d_l] history tile + Wprev_l, present only if t >= d_l.
+            // Weight-ring chunk order = consumption order of the MMA issuer (see there):
+            //   prev(0) | cur(0) res(0) prev(1) | cur(1) skip(0) res(1) prev(2) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
+            // where prev(l) = the x[t-d_l] history tile + Wprev_l, present only if t >= d_l.
             auto put_prev = [&](int t, int l, int d) {
                 if (t >= d) { put_act(ring_tile(t - d, l), DUP ? TILE / 2 : TILE); put(img + (size_t)l * im.layer_bytes, TILE); }
             };
             auto put_skip = [&](int l) {
                 for (int c = 0; c < S / 128; c++) put(img + (size_t)l * im.layer_bytes + 2 * TILE + TILE / 2 + (size_t)c * TILE, TILE);
-                if (S == 128) put(img, 16);                             // keep the chunk count even (dummy 16-byte load)
             };
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;
@@ -306,8 +303,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     if (lane == 0) TRACE(2, 100 + l);
                     if (l + 1 < L) put_cond(t, l + 1);
                     put(lw + TILE, TILE);                               // Wcur_l
-                    put(lw + 2 * TILE, TILE / 2);                       // Wres_l
                     if (l > 0) put_skip(l - 1);
+                    put(lw + 2 * TILE, TILE / 2);                       // Wres_l
                     if (l + 1 < L) put_prev(t, l + 1, dn);
                     d = dn;
                 }
@@ -320,109 +317,100 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         // =============================================================== MMA issuer (whole warp converged, one lane issues)
         {
             const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
-            uint32_t cc = 0;                                            // chunks consumed so far (ring position of the next group)
-            uint32_t ph_epi = 0;
+            int stage = 0;
+            uint32_t ph_full = 0, ph_epi = 0;
             const uint64_t d_ring = make_desc_kmajor_sw128(smem_u32(ring)), d_xc = make_desc_kmajor_sw128(smem_u32(t_xc)),
                            d_h = make_desc_kmajor_sw128(smem_u32(t_h)), d_big = make_desc_kmajor_sw128(smem_u32(t_big));
             uint32_t ph_pre = 0;
             constexpr uint64_t TILE_D = TILE >> 4;                      // one tile further, in descriptor address units
-            const uint32_t idesc256 = make_idesc_f16(128, 256);
-            // chunk number c lives in stage c % nstage; its full-barrier completes with parity (c / nstage) & 1
-            // (nstage is 6 for every supported model size; the constant lets the compiler strength-reduce % and /)
-            auto stage_of = [&](uint32_t c) -> int { return nstage == 6 ? (int)(c % 6u) : (int)(c % (uint32_t)nstage); };
-            auto par_of = [&](uint32_t c) -> uint32_t { return (nstage == 6 ? (c / 6u) : (c / (uint32_t)nstage)) & 1u; };
-            auto wait_chunk = [&](uint32_t c) -> uint64_t {
-                const int st = stage_of(c);
-                mbar_wait(&w_full[st], par_of(c));
-                return d_ring + (uint64_t)st * TILE_D;
+            auto wait_stage = [&]() -> uint64_t {                       // descriptor of the next ring stage once its data landed
+                mbar_wait(&w_full[stage], ph_full);
+                return d_ring + (uint64_t)stage * TILE_D;
             };
-            // both chunks of an adjacent pair at once: even lanes poll the first barrier, odd lanes the second
-            auto wait_pair = [&](uint32_t c) -> uint64_t {
-                const int st = stage_of(c);                              // pairs start on even stages: c+1 is st+1, same parity
-                mbar_wait(&w_full[st + (lane & 1)], par_of(c));
-                __syncwarp();
-                return d_ring + (uint64_t)st * TILE_D;
-            };
-            // 4 K-slices of one 64-deep chunk, then up to three commits; single elected lane
-            auto mma4 = [&](uint64_t da, uint64_t db, uint32_t d, uint32_t idesc, bool acc0, uint64_t* bar0, uint64_t* bar1, uint64_t* bar2) {
+            auto advance = [&]() { if (++stage == nstage) { stage = 0; ph_full ^= 1; } };
+            // 4 K-slices of one 64-deep chunk, then (optionally) up to two commits; single elected lane
+            auto mma4 = [&](uint64_t da, uint64_t db, uint32_t d, uint32_t idesc, bool acc0, uint64_t* bar0, uint64_t* bar1) {
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (acc0 || k) ? 1u : 0u);
                     if (bar0) umma_commit(bar0);
                     if (bar1) umma_commit(bar1);
-                    if (bar2) umma_commit(bar2);
                 }
                 __syncwarp();
             };
             auto wait_epi = [&]() { mbar_wait(epi_done, ph_epi); ph_epi ^= 1; tc_fence_after_sync(); };
-            // prev(l): the epilogue has initialised D1[l&1] with Lh[t][l] + Bh (tcgen05.st); add Wprev_l . x[t-d].  Chunks c, c+1.
-            auto open_layer = [&](int l, bool has_prev, uint32_t c) {
+            // open(l): the epilogue has initialised D1[l&1] with Lh[t][l] + Bh (tcgen05.st); add Wprev_l . x[t-d]
+            auto open_layer = [&](int l, bool has_prev) {
                 const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128;
                 mbar_wait(pre_done, ph_pre); ph_pre ^= 1;
                 tc_fence_after_sync();
                 if (has_prev) {
-                    const uint64_t da = wait_pair(c), db = da + TILE_D;
+                    const uint64_t da = wait_stage();
+                    const int sa = stage;
+                    advance();
+                    const uint64_t db = wait_stage();
                     tc_fence_after_sync();
-                    mma4(da, db, d1, idesc128, true, &w_empty[stage_of(c)], &w_empty[stage_of(c) + 1], nullptr);
+                    mma4(da, db, d1, idesc128, true, &w_empty[sa], &w_empty[stage]);
+                    advance();
                 }
             };
-            // skip(l): Dskip (+)= Wskip_l . h_l as ONE N=S instruction per K slice (chunks c, c+1 are adjacent in smem)
-            auto skip_layer = [&](int l, uint32_t c, uint64_t* done_bar) {
+            // skip(l): Dskip (+)= Wskip_l . h_l, h_l in the H buffer of parity l
+            auto skip_layer = [&](int l, uint64_t* done_bar) {
                 const uint64_t dh = d_h + (uint64_t)(l & 1) * TILE_D;
-                const uint64_t dw = wait_pair(c);
-                tc_fence_after_sync();
-                mma4(dh, dw, DSKIP, S == 256 ? idesc256 : idesc128, l > 0, &w_empty[stage_of(c)], &w_empty[stage_of(c) + 1], done_bar);
+                for (int c = 0; c < S / 128; c++) {
+                    const uint64_t dw = wait_stage();
+                    tc_fence_after_sync();
+                    mma4(dh, dw, DSKIP + c * 128, idesc128, l > 0, &w_empty[stage], (c == S / 128 - 1) ? done_bar : nullptr);
+                    advance();
+                }
             };
             // Issue order per layer: cur(l) | skip(l-1) in the shadow of the gate epilogue | res(l) | prev(l+1) in the shadow
             // of the residual epilogue.  Nothing but cur / res sits between an epilogue arrival and the accumulator it
-            // waits for.  Ring layout per layer group: cur, res, skip pair (l > 0), prev pair (if any) -- see the producer.
+            // waits for.
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
-                const bool hp0 = t >= 1;
-                uint32_t cprev = cc;                                    // chunks of prev(0)
-                cc += hp0 ? 2 : 0;
                 for (int l = 0; l < L; l++) {
                     int dn = d << 1; if (dn > p.maxDil) dn = 1;         // dilation of layer l + 1
                     const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128;
-                    const uint32_t c_cur = cc, c_res = cc + 1, c_skip = cc + 2;
-                    const bool hpn = (l + 1 < L) && (t >= dn);
-                    const uint32_t c_prev_next = cc + 2 + (l > 0 ? 2 : 0);
-                    cc = c_prev_next + (hpn ? 2 : 0);
-                    const uint64_t dwc = wait_pair(c_cur);              // Wcur_l and Wres_l (a pair) are in flight long before x_l
+                    uint64_t dw = 0;
+                    if (l > 0) dw = wait_stage();                       // Wcur_l is already in flight: wait for it before x_l
                     wait_epi();                                         // x_l tile ready (and, for l = 0, Dza consumed)
                     if (lane == 0) TRACE(1, 20);
-                    if (l == 0) open_layer(0, hp0, cprev);
+                    if (l == 0) { open_layer(0, t >= 1); dw = wait_stage(); }
                     tc_fence_after_sync();
-                    mma4(d_xc, dwc, d1, idesc128, true, d1_full, &w_empty[stage_of(c_cur)], nullptr);       // D1 += Wcur . x[t]
+                    mma4(d_xc, dw, d1, idesc128, true, d1_full, &w_empty[stage]);       // D1 += Wcur . x[t]
+                    advance();
                     if (lane == 0) TRACE(1, 21);
-                    if (l > 0) skip_layer(l - 1, c_skip, nullptr);      // in the shadow of the gate epilogue
-                    const uint64_t dwr = dwc + TILE_D;                  // Wres_l: second chunk of the pair
+                    if (l > 0) skip_layer(l - 1, nullptr);              // in the shadow of the gate epilogue
+                    dw = wait_stage();                                  // Wres_l
                     wait_epi();                                         // h tile ready, D1 consumed
                     if (lane == 0) TRACE(1, 22);
-                    mma4(d_h + (uint64_t)(l & 1) * TILE_D, dwr, d1, idesc64, false, dx_full, &w_empty[stage_of(c_res)], nullptr);   // Dx = Wres . h
+                    mma4(d_h + (uint64_t)(l & 1) * TILE_D, dw, d1, idesc64, false, dx_full, &w_empty[stage]);   // Dx = Wres . h
+                    advance();
                     if (lane == 0) TRACE(1, 23);
-                    if (l + 1 < L) open_layer(l + 1, hpn, c_prev_next); // in the shadow of the residual epilogue
+                    if (l + 1 < L) open_layer(l + 1, t >= dn);          // in the shadow of the residual epilogue
                     if (lane == 0) TRACE(1, 24);
                     d = dn;
                 }
-                skip_layer(L - 1, cc, skip_full);
-                cc += 2;
+                skip_layer(L - 1, skip_full);
                 wait_epi();                                             // relu(skip) tile ready
-                for (int kt = 0; kt < S / 64; kt++) {                   // Zs: one N=256 instruction per K slice
-                    const uint64_t dw = wait_pair(cc);
-                    tc_fence_after_sync();
-                    mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS, idesc256, kt > 0, &w_empty[stage_of(cc)], &w_empty[stage_of(cc) + 1],
-                         kt == S / 64 - 1 ? out_full : nullptr);
-                    cc += 2;
-                }
+                for (int kt = 0; kt < S / 64; kt++)
+                    for (int nh = 0; nh < 2; nh++) {
+                        const uint64_t dw = wait_stage();
+                        tc_fence_after_sync();
+                        const bool last = (kt == S / 64 - 1) && nh == 1;
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
+                        advance();
+                    }
                 wait_epi();                                             // relu(Zs) tile ready
-                for (int kt = 0; kt < A / 64; kt++) {
-                    const uint64_t dw = wait_pair(cc);
-                    tc_fence_after_sync();
-                    mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA, idesc256, kt > 0, &w_empty[stage_of(cc)], &w_empty[stage_of(cc) + 1],
-                         kt == A / 64 - 1 ? out_full : nullptr);
-                    cc += 2;
-                }
+                for (int kt = 0; kt < A / 64; kt++)
+                    for (int nh = 0; nh < 2; nh++) {
+                        const uint64_t dw = wait_stage();
+                        tc_fence_after_sync();
+                        const bool last = (kt == A / 64 - 1) && nh == 1;
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
+                        advance();
+                    }
             }
         }
     } else {
@@ -800,7 +788,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 
 int pick_nstage(int S, int L)
 {
-    for (int n = 8; n >= 4; n -= 2)                                // even: chunk pairs must stay adjacent (see the producer)
+    for (int n = 8; n >= 3; n--)
         if (tc_smem_bytes(S, L, n) <= 227 * 1024) return n;
     return 0;
 }
@@ -809,7 +797,7 @@ int pick_nstage(int S, int L)
 
 bool wn_tc_supported(int R_, int S, int A_, int L, int)
 {
-    return R_ == R && A_ == A && (S == 128 || S == 256) && pick_nstage(S, L) >= 4;
+    return R_ == R && A_ == A && (S == 128 || S == 256) && pick_nstage(S, L) >= 3;
 }
 
 size_t wn_tc_image_bytes(int, int S, int, int L) { return tc_image(S, L).total; }
@@ -840,7 +828,7 @@ cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream)
 cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t stream, WnLaunchInfo* info)
 {
     const int nstage = pick_nstage(p.S, p.L);
-    if (nstage < 4) return cudaErrorInvalidValue;
+    if (nstage < 3) return cudaErrorInvalidValue;
     const size_t smem = tc_smem_bytes(p.S, p.L, nstage);
     const int grid = (p.B + 127) / 128;
     cudaError_t e = cudaErrorInvalidValue;
