@@ -26,7 +26,7 @@ using namespace sm100;
 
 constexpr int R = 64, A = 256;
 constexpr int TILE = 16384;                 // [128 rows x 64 fp16] K-major SW128
-constexpr int NT = 352;                     // 8 epilogue warps + TMA producer + foreground MMA issuer + background MMA issuer
+constexpr int NT = 320;                     // 8 epilogue warps + TMA producer warp + MMA issuer warp
 constexpr int NEPI = 256;
 
 struct TcImage {                            // byte offsets inside the packed image
@@ -190,8 +190,6 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     uint64_t* pre_done = epi_done + 5;          // accumulator of the coming layer initialised with Lh + bias
     uint64_t* cond_full = epi_done + 6;         // [NC]
     uint64_t* cond_empty = epi_done + 8;        // [NC]
-    uint64_t* h_bg = epi_done + 10;             // h tile ready, for the background issuer
-    uint64_t* prev_done = epi_done + 11;        // background: Wprev GEMM of the coming layer complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 12);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -208,7 +206,6 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         mbar_init(epi_done, NEPI);
         mbar_init(d1_full, 1); mbar_init(dx_full, 1); mbar_init(skip_full, 1); mbar_init(out_full, 1);
         mbar_init(pre_done, NEPI);
-        mbar_init(h_bg, NEPI); mbar_init(prev_done, 1);
         for (int i = 0; i < NC; i++) { mbar_init(&cond_full[i], 1); mbar_init(&cond_empty[i], NEPI); }
         fence_mbar_init();
         // dilation of layer l (nv_wavenet.cuh:99-111): 1,2,4..maxDil,1,2,...
@@ -287,17 +284,14 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
                 g_cond++;
             };
-            // Weight-ring chunk order (the issuer addresses stages by chunk counter, not by arrival order):
-            //   [prev(0)] | cur(0) res(0) . . [prev(1)] | cur(1) res(1) skip(0)a skip(0)b [prev(2)] | ... | skip(L-1) | Wzs | Wza
-            // Every group is an even number of 16 KB chunks and the ring has an even number of stages, so the two chunks of
-            // a skip / output-layer pair are always adjacent in shared memory: one N=256 MMA per K slice reads both.
-            // prev(l) = the x[t-d_l] history tile + Wprev_l, present only if t >= d_l.
+            // Weight-ring chunk order = consumption order of the MMA issuer (see there):
+            //   prev(0) | cur(0) res(0) prev(1) | cur(1) skip(0) res(1) prev(2) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
+            // where prev(l) = the x[t-d_l] history tile + Wprev_l, present only if t >= d_l.
             auto put_prev = [&](int t, int l, int d) {
                 if (t >= d) { put_act(ring_tile(t - d, l), DUP ? TILE / 2 : TILE); put(img + (size_t)l * im.layer_bytes, TILE); }
             };
             auto put_skip = [&](int l) {
                 for (int c = 0; c < S / 128; c++) put(img + (size_t)l * im.layer_bytes + 2 * TILE + TILE / 2 + (size_t)c * TILE, TILE);
-                if (S == 128) put(img, 16);                             // keep the chunk count even (dummy 16-byte load)
             };
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;
@@ -309,8 +303,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     if (lane == 0) TRACE(2, 100 + l);
                     if (l + 1 < L) put_cond(t, l + 1);
                     put(lw + TILE, TILE);                               // Wcur_l
-                    put(lw + 2 * TILE, TILE / 2);                       // Wres_l
                     if (l > 0) put_skip(l - 1);
+                    put(lw + 2 * TILE, TILE / 2);                       // Wres_l
                     if (l + 1 < L) put_prev(t, l + 1, dn);
                     d = dn;
                 }
@@ -319,134 +313,105 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 for (int c = 0; c < (S / 64) * 2 + (A / 64) * 2; c++) put(ow + (size_t)c * TILE, TILE);
             }
         }
-    } else if (warp == 9 || warp == 10) {
-        // =============================================================== MMA issuers (whole warp converged, one lane issues)
-        // Two issuer warps share the tensor pipe.  FOREGROUND (warp 9) issues only what an epilogue is waiting for:
-        // cur(l), res(l) and the output layers.  BACKGROUND (warp 10) issues everything else: prev(l+1) as soon as the
-        // epilogue has pre-stored Lh+bias, and the skip GEMM of layer l as soon as h_l exists.  The long issue-blocking
-        // background groups therefore never sit between an epilogue arrival and the foreground GEMM it triggers.
-        const bool fg = (warp == 9);
-        const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64), idesc256 = make_idesc_f16(128, 256);
-        const uint64_t d_ring = make_desc_kmajor_sw128(smem_u32(ring)), d_xc = make_desc_kmajor_sw128(smem_u32(t_xc)),
-                       d_h = make_desc_kmajor_sw128(smem_u32(t_h)), d_big = make_desc_kmajor_sw128(smem_u32(t_big));
-        constexpr uint64_t TILE_D = TILE >> 4;                          // one tile further, in descriptor address units
-        // chunk number c lives in stage c % nstage; its full-barrier completes with parity (c / nstage) & 1
-        // (nstage is 6 for every supported model size; the constant lets the compiler strength-reduce % and /)
-        auto stage_of = [&](uint32_t c) -> int { return nstage == 6 ? (int)(c % 6u) : (int)(c % (uint32_t)nstage); };
-        auto par_of = [&](uint32_t c) -> uint32_t { return (nstage == 6 ? (c / 6u) : (c / (uint32_t)nstage)) & 1u; };
-        // both chunks of an adjacent pair at once: even lanes poll the first barrier, odd lanes the second
-        auto wait_pair = [&](uint32_t c) -> uint64_t {
-            const int st = stage_of(c);                                  // pairs start on even stages: c+1 is st+1, same parity
-            mbar_wait(&w_full[st + (lane & 1)], par_of(c));
-            __syncwarp();
-            return d_ring + (uint64_t)st * TILE_D;
-        };
-        // 4 K-slices of one 64-deep chunk, then up to three commits; single elected lane
-        auto mma4 = [&](uint64_t da, uint64_t db, uint32_t d, uint32_t idesc, bool acc0, uint64_t* bar0, uint64_t* bar1, uint64_t* bar2) {
-            if (elect_one()) {
+    } else if (warp == 9) {
+        // =============================================================== MMA issuer (whole warp converged, one lane issues)
+        {
+            const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
+            int stage = 0;
+            uint32_t ph_full = 0, ph_epi = 0;
+            const uint64_t d_ring = make_desc_kmajor_sw128(smem_u32(ring)), d_xc = make_desc_kmajor_sw128(smem_u32(t_xc)),
+                           d_h = make_desc_kmajor_sw128(smem_u32(t_h)), d_big = make_desc_kmajor_sw128(smem_u32(t_big));
+            uint32_t ph_pre = 0;
+            constexpr uint64_t TILE_D = TILE >> 4;                      // one tile further, in descriptor address units
+            auto wait_stage = [&]() -> uint64_t {                       // descriptor of the next ring stage once its data landed
+                mbar_wait(&w_full[stage], ph_full);
+                return d_ring + (uint64_t)stage * TILE_D;
+            };
+            auto advance = [&]() { if (++stage == nstage) { stage = 0; ph_full ^= 1; } };
+            // 4 K-slices of one 64-deep chunk, then (optionally) up to two commits; single elected lane
+            auto mma4 = [&](uint64_t da, uint64_t db, uint32_t d, uint32_t idesc, bool acc0, uint64_t* bar0, uint64_t* bar1) {
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (acc0 || k) ? 1u : 0u);
-                if (bar0) umma_commit(bar0);
-                if (bar1) umma_commit(bar1);
-                if (bar2) umma_commit(bar2);
-            }
-            __syncwarp();
-        };
-        uint32_t cc = 0;                                                // ring position of the next chunk group (both issuers count alike)
-        uint32_t ph_a = 0, ph_b = 0;                                    // fg: epi_done / prev_done     bg: h_bg / pre_done
-        for (int t = t_begin; t < t_end; t++) {
-            int d = 1;                                                  // dilation of layer l (nv_wavenet.cuh:99-111)
-            const bool hp0 = t >= 1;
-            const uint32_t cprev0 = cc;
-            cc += hp0 ? 2 : 0;
-            if (!fg) {
-                // prev(0): D1[0] (pre-stored Lh + Bh) += Wprev_0 . x[t-1]
-                mbar_wait(pre_done, ph_b); ph_b ^= 1;
-                tc_fence_after_sync();
-                if (hp0) {
-                    const uint64_t da = wait_pair(cprev0);
-                    tc_fence_after_sync();
-                    mma4(da, da + TILE_D, D1B, idesc128, true, &w_empty[stage_of(cprev0)], &w_empty[stage_of(cprev0) + 1], prev_done);
-                } else {
-                    if (elect_one()) mbar_arrive(prev_done);
-                    __syncwarp();
+                    for (int k = 0; k < 4; k++) umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (acc0 || k) ? 1u : 0u);
+                    if (bar0) umma_commit(bar0);
+                    if (bar1) umma_commit(bar1);
                 }
-            }
-            for (int l = 0; l < L; l++) {
-                int dn = d << 1; if (dn > p.maxDil) dn = 1;             // dilation of layer l + 1
+                __syncwarp();
+            };
+            auto wait_epi = [&]() { mbar_wait(epi_done, ph_epi); ph_epi ^= 1; tc_fence_after_sync(); };
+            // open(l): the epilogue has initialised D1[l&1] with Lh[t][l] + Bh (tcgen05.st); add Wprev_l . x[t-d]
+            auto open_layer = [&](int l, bool has_prev) {
                 const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128;
-                const uint32_t c_cur = cc, c_skip = cc + 2;             // group l: cur, res, [skip(l-1) pair], [prev(l+1) pair]
-                const bool hpn = (l + 1 < L) && (t >= dn);
-                const uint32_t c_prev_next = cc + 2 + (l > 0 ? 2 : 0);
-                cc = c_prev_next + (hpn ? 2 : 0);
-                if (fg) {
-                    const uint64_t dwc = wait_pair(c_cur);              // Wcur_l and Wres_l (a pair) are in flight long before x_l
-                    mbar_wait(epi_done, ph_a); ph_a ^= 1;               // x_l tile ready (and, for l = 0, Dza consumed)
-                    mbar_wait(prev_done, ph_b); ph_b ^= 1;              // D1[l&1] holds Lh + Bh (+ Wprev.x[t-d])
+                mbar_wait(pre_done, ph_pre); ph_pre ^= 1;
+                tc_fence_after_sync();
+                if (has_prev) {
+                    const uint64_t da = wait_stage();
+                    const int sa = stage;
+                    advance();
+                    const uint64_t db = wait_stage();
                     tc_fence_after_sync();
+                    mma4(da, db, d1, idesc128, true, &w_empty[sa], &w_empty[stage]);
+                    advance();
+                }
+            };
+            // skip(l): Dskip (+)= Wskip_l . h_l, h_l in the H buffer of parity l
+            auto skip_layer = [&](int l, uint64_t* done_bar) {
+                const uint64_t dh = d_h + (uint64_t)(l & 1) * TILE_D;
+                for (int c = 0; c < S / 128; c++) {
+                    const uint64_t dw = wait_stage();
+                    tc_fence_after_sync();
+                    mma4(dh, dw, DSKIP + c * 128, idesc128, l > 0, &w_empty[stage], (c == S / 128 - 1) ? done_bar : nullptr);
+                    advance();
+                }
+            };
+            // Issue order per layer: cur(l) | skip(l-1) in the shadow of the gate epilogue | res(l) | prev(l+1) in the shadow
+            // of the residual epilogue.  Nothing but cur / res sits between an epilogue arrival and the accumulator it
+            // waits for.
+            for (int t = t_begin; t < t_end; t++) {
+                int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
+                for (int l = 0; l < L; l++) {
+                    int dn = d << 1; if (dn > p.maxDil) dn = 1;         // dilation of layer l + 1
+                    const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128;
+                    uint64_t dw = 0;
+                    if (l > 0) dw = wait_stage();                       // Wcur_l is already in flight: wait for it before x_l
+                    wait_epi();                                         // x_l tile ready (and, for l = 0, Dza consumed)
                     if (lane == 0) TRACE(1, 20);
-                    mma4(d_xc, dwc, d1, idesc128, true, d1_full, &w_empty[stage_of(c_cur)], nullptr);       // D1 += Wcur . x[t]
+                    if (l == 0) { open_layer(0, t >= 1); dw = wait_stage(); }
+                    tc_fence_after_sync();
+                    mma4(d_xc, dw, d1, idesc128, true, d1_full, &w_empty[stage]);       // D1 += Wcur . x[t]
+                    advance();
                     if (lane == 0) TRACE(1, 21);
-                    mbar_wait(epi_done, ph_a); ph_a ^= 1;               // h tile ready, D1 drained
-                    tc_fence_after_sync();
+                    if (l > 0) skip_layer(l - 1, nullptr);              // in the shadow of the gate epilogue
+                    dw = wait_stage();                                  // Wres_l
+                    wait_epi();                                         // h tile ready, D1 consumed
                     if (lane == 0) TRACE(1, 22);
-                    mma4(d_h + (uint64_t)(l & 1) * TILE_D, dwc + TILE_D, d1, idesc64, false, dx_full, &w_empty[stage_of(c_cur) + 1], nullptr);   // Dx = Wres . h
+                    mma4(d_h + (uint64_t)(l & 1) * TILE_D, dw, d1, idesc64, false, dx_full, &w_empty[stage]);   // Dx = Wres . h
+                    advance();
                     if (lane == 0) TRACE(1, 23);
-                } else {
-                    // skip(l-1) could not start before its weights arrive with group l; h_{l-1} is long there
-                    if (l > 0) {
-                        const uint64_t dw = wait_pair(c_skip);
+                    if (l + 1 < L) open_layer(l + 1, t >= dn);          // in the shadow of the residual epilogue
+                    if (lane == 0) TRACE(1, 24);
+                    d = dn;
+                }
+                skip_layer(L - 1, skip_full);
+                wait_epi();                                             // relu(skip) tile ready
+                for (int kt = 0; kt < S / 64; kt++)
+                    for (int nh = 0; nh < 2; nh++) {
+                        const uint64_t dw = wait_stage();
                         tc_fence_after_sync();
-                        mma4(d_h + (uint64_t)((l - 1) & 1) * TILE_D, dw, DSKIP, S == 256 ? idesc256 : idesc128, l > 1,
-                             &w_empty[stage_of(c_skip)], &w_empty[stage_of(c_skip) + 1], skip_full);
+                        const bool last = (kt == S / 64 - 1) && nh == 1;
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
+                        advance();
                     }
-                    mbar_wait(h_bg, ph_a); ph_a ^= 1;                   // h_l exists (keeps this warp in step with the layers)
-                    if (l + 1 < L) {
-                        mbar_wait(pre_done, ph_b); ph_b ^= 1;           // D1[(l+1)&1] pre-stored with Lh + Bh
+                wait_epi();                                             // relu(Zs) tile ready
+                for (int kt = 0; kt < A / 64; kt++)
+                    for (int nh = 0; nh < 2; nh++) {
+                        const uint64_t dw = wait_stage();
                         tc_fence_after_sync();
-                        if (hpn) {
-                            const uint64_t da = wait_pair(c_prev_next);
-                            tc_fence_after_sync();
-                            mma4(da, da + TILE_D, D1B + (uint32_t)((l + 1) & 1) * 128, idesc128, true,
-                                 &w_empty[stage_of(c_prev_next)], &w_empty[stage_of(c_prev_next) + 1], prev_done);
-                        } else {
-                            if (elect_one()) mbar_arrive(prev_done);
-                            __syncwarp();
-                        }
+                        const bool last = (kt == A / 64 - 1) && nh == 1;
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
+                        advance();
                     }
-                }
-                d = dn;
             }
-            // group after the layers: skip(L-1) pair, then the output layers
-            if (!fg) {
-                const uint64_t dw = wait_pair(cc);
-                tc_fence_after_sync();
-                mma4(d_h + (uint64_t)((L - 1) & 1) * TILE_D, dw, DSKIP, S == 256 ? idesc256 : idesc128, L > 1,
-                     &w_empty[stage_of(cc)], &w_empty[stage_of(cc) + 1], skip_full);
-            }
-            cc += 2;
-            if (fg) {
-                mbar_wait(epi_done, ph_a); ph_a ^= 1;                   // relu(skip) tile ready
-                tc_fence_after_sync();
-                for (int kt = 0; kt < S / 64; kt++) {                   // Zs: one N=256 instruction per K slice
-                    const uint64_t dw = wait_pair(cc + 2 * kt);
-                    tc_fence_after_sync();
-                    mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS, idesc256, kt > 0, &w_empty[stage_of(cc + 2 * kt)], &w_empty[stage_of(cc + 2 * kt) + 1],
-                         kt == S / 64 - 1 ? out_full : nullptr);
-                }
-            }
-            cc += 2 * (S / 64);
-            if (fg) {
-                mbar_wait(epi_done, ph_a); ph_a ^= 1;                   // relu(Zs) tile ready
-                tc_fence_after_sync();
-                for (int kt = 0; kt < A / 64; kt++) {
-                    const uint64_t dw = wait_pair(cc + 2 * kt);
-                    tc_fence_after_sync();
-                    mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA, idesc256, kt > 0, &w_empty[stage_of(cc + 2 * kt)], &w_empty[stage_of(cc + 2 * kt) + 1],
-                         kt == A / 64 - 1 ? out_full : nullptr);
-                }
-            }
-            cc += 2 * (A / 64);
         }
     } else {
         // =============================================================== epilogue: 8 warps, TWO threads per utterance
@@ -619,26 +584,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     for (int q = 0; q < CQ; q++) st_tile(th, q4 + q, make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]));
                 }
                 if (tid == 0) TRACE(0, 12);
-                if (l > 0) {
-                    // skip(l-1) (background issuer) has drained H[(l-1)&1] -- the buffer the NEXT gate overwrites -- and the skip
-                    // sum holds layers 0..l-1 exactly until h_l is published: the per-layer dump needs no extra barrier
-                    mbar_wait(skip_full, ph_skip); ph_skip ^= 1;
-                    tc_fence_after_sync();
-                    if (dump && wv) {
-                        const int c_lo = sub * (S / NS);
-                        for (int c0 = c_lo; c0 < c_lo + S / NS; c0 += 16) {
-                            uint32_t w[16];
-                            tmem_ld16(DSKIP + lane_off + c0, w);
-                            tmem_ld_wait();
-                            if (valid)
-                                for (int j = 0; j < 16; j++)
-                                    p.skipOut[((size_t)(l - 1) * B + b) * S + c0 + j] = __uint_as_float(w[j]) + gbias[im.b_bskp + (size_t)(l - 1) * S + c0 + j];
-                        }
-                        tc_fence_before_sync();
-                    }
-                }
                 publish();                                              // h ready, D1 drained
-                mbar_arrive(h_bg);
                 if (tid == 0) TRACE(0, 3);
                 if (l + 1 < L) prestore(l + 1);                         // while the residual GEMM runs
                 // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
@@ -667,6 +613,19 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         if (valid) {
 #pragma unroll
                             for (int j = 0; j < CW; j++) p.xtOut[((size_t)l * B + b) * R + c32 + j] = x[j];
+                        }
+                        // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
+                        // next contribution is only issued after the arrival below: no extra barrier needed
+                        if (l > 0) {
+                            const int c_lo = sub * (S / NS);
+                            for (int c0 = c_lo; c0 < c_lo + S / NS; c0 += 16) {
+                                uint32_t w[16];
+                                tmem_ld16(DSKIP + lane_off + c0, w);
+                                tmem_ld_wait();
+                                if (valid)
+                                    for (int j = 0; j < 16; j++)
+                                        p.skipOut[((size_t)(l - 1) * B + b) * S + c0 + j] = __uint_as_float(w[j]) + gbias[im.b_bskp + (size_t)(l - 1) * S + c0 + j];
+                            }
                         }
                     }
                 }
@@ -829,7 +788,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 
 int pick_nstage(int S, int L)
 {
-    for (int n = 8; n >= 4; n -= 2)                                // even: chunk pairs must stay adjacent (see the producer)
+    for (int n = 8; n >= 3; n--)
         if (tc_smem_bytes(S, L, n) <= 227 * 1024) return n;
     return 0;
 }
@@ -838,7 +797,7 @@ int pick_nstage(int S, int L)
 
 bool wn_tc_supported(int R_, int S, int A_, int L, int)
 {
-    return R_ == R && A_ == A && (S == 128 || S == 256) && pick_nstage(S, L) >= 4;
+    return R_ == R && A_ == A && (S == 128 || S == 256) && pick_nstage(S, L) >= 3;
 }
 
 size_t wn_tc_image_bytes(int, int S, int, int L) { return tc_image(S, L).total; }
@@ -869,7 +828,7 @@ cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream)
 cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t stream, WnLaunchInfo* info)
 {
     const int nstage = pick_nstage(p.S, p.L);
-    if (nstage < 4) return cudaErrorInvalidValue;
+    if (nstage < 3) return cudaErrorInvalidValue;
     const size_t smem = tc_smem_bytes(p.S, p.L, nstage);
     const int grid = (p.B + 127) / 128;
     cudaError_t e = cudaErrorInvalidValue;
