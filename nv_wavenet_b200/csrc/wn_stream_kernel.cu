@@ -77,58 +77,6 @@ __device__ __forceinline__ void dot_cols(const TD* __restrict__ W, int M, int K,
     }
 }
 
-// Weight columns [0, KP) of `row`, requested one stage ahead of their use (weights do not depend on data): the L2 latency
-// of the next stage's weights is hidden behind the current stage's arithmetic.
-template <typename TD, int KP>
-__device__ __forceinline__ void preload_cols(const TD* __restrict__ W, int M, int row, TD (&w)[KP])
-{
-    const TD* wp = W + row;
-#pragma unroll
-    for (int j = 0; j < KP; j++) w[j] = __ldg(wp + (size_t)j * M);
-}
-
-template <typename TD> __device__ __forceinline__ float to_f(TD v);
-template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
-
-// dot product whose first KP weight columns were preloaded; identical summation order to dot_cols
-template <typename TD, int BT, int KP, int KB>
-__device__ __forceinline__ void dot_pre(const TD (&wpre)[KP], const TD* __restrict__ W, int M, int K, int row,
-                                        const float* __restrict__ xs, float (&acc)[BT])
-{
-    using N = Num<TD>;
-#pragma unroll
-    for (int b = 0; b < BT; b++) acc[b] = 0.f;
-#pragma unroll
-    for (int j = 0; j < KP; j += 4) {
-#pragma unroll
-        for (int b = 0; b < BT; b++) {
-            const float4 xa = *reinterpret_cast<const float4*>(xs + b * K + j);
-            float a = acc[b];
-            a = N::mac(a, to_f(wpre[j]), xa.x); a = N::mac(a, to_f(wpre[j + 1]), xa.y);
-            a = N::mac(a, to_f(wpre[j + 2]), xa.z); a = N::mac(a, to_f(wpre[j + 3]), xa.w);
-            acc[b] = a;
-        }
-    }
-    const TD* wp = W + row;
-#pragma unroll 1
-    for (int k0 = KP; k0 < K; k0 += KB) {
-        float w[KB];
-#pragma unroll
-        for (int j = 0; j < KB; j++) w[j] = N::ld(wp + (size_t)(k0 + j) * M);
-#pragma unroll
-        for (int j = 0; j < KB; j += 4) {
-#pragma unroll
-            for (int b = 0; b < BT; b++) {
-                const float4 xa = *reinterpret_cast<const float4*>(xs + b * K + k0 + j);
-                float a = acc[b];
-                a = N::mac(a, w[j], xa.x); a = N::mac(a, w[j + 1], xa.y); a = N::mac(a, w[j + 2], xa.z); a = N::mac(a, w[j + 3], xa.w);
-                acc[b] = a;
-            }
-        }
-    }
-}
-
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 template <int R, int S> struct Shape {
@@ -149,8 +97,6 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
     constexpr int NACT = 2 * R * BT;
     constexpr int ACT_PER = (NACT + NT - 1) / NT;
     constexpr int KBR = R < 64 ? R : 64;          // weight columns in flight per thread in the R-deep dots
-    constexpr int KP = R <= 64 ? R : 32;          // ... of which this many are requested one stage ahead (register double buffer)
-    constexpr int KPO = 32;                       // same for the output layers
     static_assert(R * BT <= NT, "one x-task per thread");
 
     const int tid = threadIdx.x;
@@ -203,14 +149,6 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
     const int xb = has_x ? tid / R : 0, xr = has_x ? tid % R : 0;
 
     const int t_end = p.init_sample + p.count;
-    // software pipeline of the weight stream: w1 = this thread's stage-1 row of the coming layer, w3 = its stage-3 row,
-    // wo = its first output-layer row; each is requested while the previous stage computes
-    TD w1[KP], w3[KP], wo[KPO];
-    const bool s1_cur = tid >= 2 * R;
-    const int s1_row = s1_cur ? tid - 2 * R : tid;
-    const bool s3_res = tid < R;
-    const int s3_row = s3_res ? tid : tid - R;
-    if (tid < 4 * R) preload_cols<TD, KP>(s1_cur ? Wcur : Wprev, 2 * R, s1_row, w1);
     auto ring_at = [&](int t, int l, int b, int r) -> TD* {
         return ring + (((size_t)(t % slots) * L + l) * B + (b0 + b)) * R + r;
     };
@@ -270,13 +208,12 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
             }
 
             // ---- stage 1: a_prev = Wprev.x[t-d], a_cur = Wcur.x[t]  (reference.cpp:61-65) ----
-            if (tid < R + S) preload_cols<TD, KP>(s3_res ? Wres + (size_t)l * R * R : Wskip + (size_t)l * S * R, s3_res ? R : S, s3_row, w3);
             if (tid < 4 * R) {
-                const bool cur = s1_cur;
-                const int row = s1_row;
+                const bool cur = tid >= 2 * R;
+                const int row = cur ? tid - 2 * R : tid;
                 const TD* W = (cur ? Wcur : Wprev) + (size_t)l * 2 * R * R;
                 float acc[BT];
-                dot_pre<TD, BT, KP, KBR>(w1, W, 2 * R, R, row, cur ? xq : xp, acc);
+                dot_cols<TD, BT, KBR>(W, 2 * R, R, row, cur ? xq : xp, acc);
                 float* dst = cur ? ac : ap;
 #pragma unroll
                 for (int b = 0; b < BT; b++) dst[b * 2 * R + row] = acc[b];
@@ -306,18 +243,13 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
             __syncthreads();
 
             // ---- stage 3: residual (reference.cpp:82-84) and skip (reference.cpp:86-90) ----
-            if (l + 1 < L) {
-                if (tid < 4 * R) preload_cols<TD, KP>((s1_cur ? Wcur : Wprev) + (size_t)(l + 1) * 2 * R * R, 2 * R, s1_row, w1);
-            } else if (tid < A) {
-                preload_cols<TD, KPO>(Wzs, A, tid, wo);
-            }
             if (tid < R + S) {
                 const bool is_res = tid < R;
                 const int row = is_res ? tid : tid - R;
                 const TD* W = is_res ? Wres + (size_t)l * R * R : Wskip + (size_t)l * S * R;
                 const float bias = is_res ? N::ld(Bres + (size_t)l * R + row) : N::ld(Bskip + (size_t)l * S + row);
                 float acc[BT];
-                dot_pre<TD, BT, KP, KBR>(w3, W, is_res ? R : S, R, row, hq, acc);
+                dot_cols<TD, BT, KBR>(W, is_res ? R : S, R, row, hq, acc);
                 if (is_res) {
 #pragma unroll
                     for (int b = 0; b < BT; b++) {
@@ -346,12 +278,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
         for (int row = tid; row < A; row += NT) {
             float acc[BT];
             const float bias = N::ld(Bzs + row);
-            if (row == tid) {                                           // first (usually only) row of this thread: head preloaded
-                dot_pre<TD, BT, KPO, 32>(wo, Wzs, A, S, row, skq, acc);
-                preload_cols<TD, KPO>(Wza, A, tid, wo);                  // head of the second output layer
-            } else {
-                dot_cols<TD, BT, 32>(Wzs, A, S, row, skq, acc);
-            }
+            dot_cols<TD, BT, 32>(Wzs, A, S, row, skq, acc);
 #pragma unroll
             for (int b = 0; b < BT; b++) {
                 float v = N::add(acc[b], bias);
@@ -361,12 +288,10 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
             }
         }
         __syncthreads();
-        if (tid < 4 * R) preload_cols<TD, KP>(s1_cur ? Wcur : Wprev, 2 * R, s1_row, w1);      // layer 0 of the next sample
         for (int row = tid; row < A; row += NT) {
             float acc[BT];
             const float bias = N::ld(Bza + row);
-            if (row == tid) dot_pre<TD, BT, KPO, 32>(wo, Wza, A, A, row, zsq, acc);
-            else dot_cols<TD, BT, 32>(Wza, A, A, row, zsq, acc);
+            dot_cols<TD, BT, 32>(Wza, A, A, row, zsq, acc);
 #pragma unroll
             for (int b = 0; b < BT; b++) {
                 const float v = N::add(acc[b], bias);
