@@ -218,3 +218,34 @@ def test_wavenet_infer_c_abi_drop_in():
     w2 = dict(w); w2["selectors"] = sel; w2["Bzs"] = np.zeros(A, np.float32); w2["Bza"] = np.zeros(A, np.float32)
     o = cpu_oracle(w2, L, B, N, R, S, A, md)
     assert np.array_equal(samples, o.run(N, B))
+
+
+def test_nvwavenet_python_class_matches_oracle():
+    """pytorch/nv_wavenet.py surface (NVWaveNet(**export_weights()).infer(cond_input, impl)): conv-style weight shapes,
+    one extra (unused) residual layer appended, cond_input channels x batch x layers x samples; device tensors."""
+    import torch
+    from nv_wavenet_b200.nv_wavenet import Impl, NVWaveNet
+    R, S, A, L, B, N, md = 64, 256, 256, 3, 2, 12, 4
+    w = refgen.lively_inputs(123, R, S, A, L, B, N)
+    dev = "cuda"
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cm = lambda flat, M, K: np.ascontiguousarray(flat.reshape(K, M).T)             # column-major flat -> row-major [M][K]
+    dilate = [tt(np.stack([cm(w["Wprev"][l], 2 * R, R), cm(w["Wcur"][l], 2 * R, R)], axis=2)) for l in range(L)]
+    net = NVWaveNet(embedding_prev=tt(w["embPrev"]), embedding_curr=tt(w["embCur"]),
+                    conv_out_weight=tt(cm(w["Wzs"], A, S)[:, :, None]), conv_end_weight=tt(cm(w["Wza"], A, A)[:, :, None]),
+                    dilate_weights=dilate, dilate_biases=[tt(w["Bh"][l]) for l in range(L)], max_dilation=md,
+                    res_weights=[tt(cm(w["Wres"][l], R, R)[:, :, None]) for l in range(L - 1)],
+                    res_biases=[tt(w["Bres"][l]) for l in range(L - 1)],
+                    skip_weights=[tt(cm(w["Wskip"][l], S, R)[:, :, None]) for l in range(L)],
+                    skip_biases=[tt(w["Bskip"][l]) for l in range(L)], use_embed_tanh=True)
+    cond = tt(np.ascontiguousarray(w["Lh"].transpose(3, 2, 1, 0)))               # [2R][B][L][N]
+    C.CDLL(None).srand(99)
+    y = net.infer(cond, Impl.PERSISTENT).cpu().numpy()
+    rng = refgen.GlibcRand(99)
+    w2 = dict(w)
+    w2["selectors"] = refgen.randomize(rng, B, N, np.float32(0.5), np.float32(1.0)).reshape(N, B)
+    w2["Bzs"] = np.zeros(A, np.float32); w2["Bza"] = np.zeros(A, np.float32)
+    w2["Wres"] = w["Wres"].copy(); w2["Bres"] = w["Bres"].copy()
+    w2["Wres"][L - 1] = 0; w2["Bres"][L - 1] = 0                                # the appended, unused last residual layer
+    o = cpu_oracle(w2, L, B, N, R, S, A, md)
+    assert np.array_equal(y, o.run(N, B))
