@@ -248,8 +248,37 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         {
             int stage = 0;
             uint32_t ph = 1;
+            // Conditioning tiles have their own buffers and barriers.  They are issued opportunistically ("pumped") whenever
+            // a buffer is free -- never with a blocking wait, so a busy conditioning buffer can not hold up the weight stream
+            // (and the weight stream can not hold up conditioning: the wait loops below keep pumping).
+            int g_cond = 0;                                             // next tile to request: t = t_begin + g / L, l = g % L
+            const int g_total = (t_end - t_begin) * L;
+            int g_allow = 0;                                            // tiles [0, g_allow) may be requested (look-ahead policy)
+            auto pump_cond = [&]() {
+                while (g_cond < g_allow && g_cond < g_total) {
+                    const int cbuf = g_cond % NC;
+                    if (!mbar_try_wait(&cond_empty[cbuf], ((g_cond / NC) & 1) ^ 1)) break;
+                    const int tt = t_begin + g_cond / L, ll = g_cond % L;
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&cond_full[cbuf], 2 * c_bytes);
+                        tma_load_1d(t_cond + (size_t)cbuf * CB, cond_ptr(tt, ll, 0), 2 * c_bytes, &cond_full[cbuf]);   // both halves are contiguous
+                        const int gp = g_cond + 4;                      // pull the tiles a few layers ahead from HBM into L2
+                        if (gp < g_total) tma_prefetch_l2(cond_ptr(t_begin + gp / L, gp % L, 0), 2 * c_bytes);
+                    }
+                    __syncwarp();
+                    g_cond++;
+                }
+            };
+            auto wait_empty = [&]() {
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&w_empty[stage], ph)) {
+                    pump_cond();
+                    if (++spins > (1u << 26)) mbar_timeout(smem_u32(&w_empty[stage]), ph);
+                }
+            };
             auto put = [&](const void* src, uint32_t bytes) {
-                mbar_wait(&w_empty[stage], ph);
+                pump_cond();
+                wait_empty();
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&w_full[stage], bytes);
                     tma_load_1d(ring + (size_t)stage * TILE, src, bytes, &w_full[stage]);
@@ -260,7 +289,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             // history tile: `bytes` of rows from row 0; with DUP the same rows again from row 64
             auto put_act = [&](const void* src, uint32_t bytes) {
                 if (!DUP) { put(src, bytes); return; }
-                mbar_wait(&w_empty[stage], ph);
+                pump_cond();
+                wait_empty();
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&w_full[stage], 2 * bytes);
                     tma_load_1d(ring + (size_t)stage * TILE, src, bytes, &w_full[stage]);
@@ -268,21 +298,6 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 }
                 __syncwarp();
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
-            };
-            // conditioning tile g (g counts layers since the start of the launch) -> buffer g % NC
-            int g_cond = 0;
-            auto put_cond = [&](int t, int l) {
-                const int cbuf = g_cond % NC;
-                mbar_wait(&cond_empty[cbuf], ((g_cond / NC) & 1) ^ 1);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&cond_full[cbuf], 2 * c_bytes);
-                    tma_load_1d(t_cond + (size_t)cbuf * CB, cond_ptr(t, l, 0), 2 * c_bytes, &cond_full[cbuf]);   // both halves are contiguous
-                    // pull the tiles a few layers ahead from HBM into L2
-                    int tl = t * L + l + 4;
-                    if (tl < t_end * L) tma_prefetch_l2(cond_ptr(tl / L, tl % L, 0), 2 * c_bytes);
-                }
-                __syncwarp();
-                g_cond++;
             };
             // Weight-ring chunk order = consumption order of the MMA issuer (see there):
             //   prev(0) | cur(0) prev(1) res(0) skip(0) | cur(1) prev(2) res(1) skip(1) | ... | cur(L-1) res(L-1) skip(L-1) | Wzs | Wza
@@ -295,19 +310,14 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             };
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;
-                // conditioning tiles run two layers ahead of the weights, across the sample boundary
-                if (t == t_begin) put_cond(t, 0);
+                // conditioning tiles may run up to three layers ahead of the weights, across the sample boundary
+                g_allow = (t - t_begin) * L + 2;
                 put_prev(t, 0, 1);
-                if (t == t_begin && L > 1) put_cond(t, 1);
                 for (int l = 0; l < L; l++) {
                     const unsigned char* lw = img + (size_t)l * im.layer_bytes;
                     int dn = d << 1; if (dn > p.maxDil) dn = 1;
                     if (lane == 0) TRACE(2, 100 + l);
-                    {
-                        const int q = l + 2;                            // tile index two layers ahead
-                        if (L > 1) { if (q < L) put_cond(t, q); else if (t + 1 < t_end) put_cond(t + 1, q - L); }
-                        else if (t + 1 < t_end && l == 0) put_cond(t + 1, 0);
-                    }
+                    g_allow = (t - t_begin) * L + l + 3;
                     put(lw + TILE, TILE);                               // Wcur_l
                     if (l + 1 < L) put_prev(t, l + 1, dn);
                     put(lw + 2 * TILE, TILE / 2);                       // Wres_l
