@@ -248,37 +248,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         {
             int stage = 0;
             uint32_t ph = 1;
-            // Conditioning tiles have their own buffers and barriers.  They are issued opportunistically ("pumped") whenever
-            // a buffer is free -- never with a blocking wait, so a busy conditioning buffer can not hold up the weight stream
-            // (and the weight stream can not hold up conditioning: the wait loops below keep pumping).
-            int g_cond = 0;                                             // next tile to request: t = t_begin + g / L, l = g % L
-            const int g_total = (t_end - t_begin) * L;
-            int g_allow = 0;                                            // tiles [0, g_allow) may be requested (look-ahead policy)
-            auto pump_cond = [&]() {
-                while (g_cond < g_allow && g_cond < g_total) {
-                    const int cbuf = g_cond % NC;
-                    if (!mbar_try_wait(&cond_empty[cbuf], ((g_cond / NC) & 1) ^ 1)) break;
-                    const int tt = t_begin + g_cond / L, ll = g_cond % L;
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(&cond_full[cbuf], 2 * c_bytes);
-                        tma_load_1d(t_cond + (size_t)cbuf * CB, cond_ptr(tt, ll, 0), 2 * c_bytes, &cond_full[cbuf]);   // both halves are contiguous
-                        const int gp = g_cond + 4;                      // pull the tiles a few layers ahead from HBM into L2
-                        if (gp < g_total) tma_prefetch_l2(cond_ptr(t_begin + gp / L, gp % L, 0), 2 * c_bytes);
-                    }
-                    __syncwarp();
-                    g_cond++;
-                }
-            };
-            auto wait_empty = [&]() {
-                uint32_t spins = 0;
-                while (!mbar_try_wait(&w_empty[stage], ph)) {
-                    pump_cond();
-                    if (++spins > (1u << 26)) mbar_timeout(smem_u32(&w_empty[stage]), ph);
-                }
-            };
             auto put = [&](const void* src, uint32_t bytes) {
-                pump_cond();
-                wait_empty();
+                mbar_wait(&w_empty[stage], ph);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&w_full[stage], bytes);
                     tma_load_1d(ring + (size_t)stage * TILE, src, bytes, &w_full[stage]);
@@ -289,8 +260,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             // history tile: `bytes` of rows from row 0; with DUP the same rows again from row 64
             auto put_act = [&](const void* src, uint32_t bytes) {
                 if (!DUP) { put(src, bytes); return; }
-                pump_cond();
-                wait_empty();
+                mbar_wait(&w_empty[stage], ph);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&w_full[stage], 2 * bytes);
                     tma_load_1d(ring + (size_t)stage * TILE, src, bytes, &w_full[stage]);
@@ -299,8 +269,23 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 __syncwarp();
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
             };
+            // conditioning tile g (g counts layers since the start of the launch) -> buffer g % NC
+            int g_cond = 0;
+            auto put_cond = [&](int t, int l) {
+                const int cbuf = g_cond % NC;
+                mbar_wait(&cond_empty[cbuf], ((g_cond / NC) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&cond_full[cbuf], 2 * c_bytes);
+                    tma_load_1d(t_cond + (size_t)cbuf * CB, cond_ptr(t, l, 0), 2 * c_bytes, &cond_full[cbuf]);   // both halves are contiguous
+                    // pull the tiles a few layers ahead from HBM into L2
+                    int tl = t * L + l + 4;
+                    if (tl < t_end * L) tma_prefetch_l2(cond_ptr(tl / L, tl % L, 0), 2 * c_bytes);
+                }
+                __syncwarp();
+                g_cond++;
+            };
             // Weight-ring chunk order = consumption order of the MMA issuer (see there):
-            //   prev(0) | cur(0) prev(1) res(0) skip(0) | cur(1) prev(2) res(1) skip(1) | ... | cur(L-1) res(L-1) skip(L-1) | Wzs | Wza
+            //   prev(0) | cur(0) res(0) prev(1) | cur(1) skip(0) res(1) prev(2) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
             // where prev(l) = the x[t-d_l] history tile + Wprev_l, present only if t >= d_l.
             auto put_prev = [&](int t, int l, int d) {
                 if (t >= d) { put_act(ring_tile(t - d, l), DUP ? TILE / 2 : TILE); put(img + (size_t)l * im.layer_bytes, TILE); }
@@ -310,20 +295,20 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             };
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;
-                // conditioning tiles may run up to three layers ahead of the weights, across the sample boundary
-                g_allow = (t - t_begin) * L + 2;
+                put_cond(t, 0);
                 put_prev(t, 0, 1);
                 for (int l = 0; l < L; l++) {
                     const unsigned char* lw = img + (size_t)l * im.layer_bytes;
                     int dn = d << 1; if (dn > p.maxDil) dn = 1;
                     if (lane == 0) TRACE(2, 100 + l);
-                    g_allow = (t - t_begin) * L + l + 3;
+                    if (l + 1 < L) put_cond(t, l + 1);
                     put(lw + TILE, TILE);                               // Wcur_l
-                    if (l + 1 < L) put_prev(t, l + 1, dn);
+                    if (l > 0) put_skip(l - 1);
                     put(lw + 2 * TILE, TILE / 2);                       // Wres_l
-                    put_skip(l);
+                    if (l + 1 < L) put_prev(t, l + 1, dn);
                     d = dn;
                 }
+                put_skip(L - 1);
                 const unsigned char* ow = img + im.off_out;
                 for (int c = 0; c < (S / 64) * 2 + (A / 64) * 2; c++) put(ow + (size_t)c * TILE, TILE);
             }
@@ -379,9 +364,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     advance();
                 }
             };
-            // Issue order per layer: cur(l) | prev(l+1) in the shadow of the gate epilogue | res(l) | skip(l) in the shadow
+            // Issue order per layer: cur(l) | skip(l-1) in the shadow of the gate epilogue | res(l) | prev(l+1) in the shadow
             // of the residual epilogue.  Nothing but cur / res sits between an epilogue arrival and the accumulator it
-            // waits for, and each background GEMM is about as long as the epilogue stage it hides behind.
+            // waits for.
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
                 for (int l = 0; l < L; l++) {
@@ -396,17 +381,18 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     mma4(d_xc, dw, d1, idesc128, true, d1_full, &w_empty[stage]);       // D1 += Wcur . x[t]
                     advance();
                     if (lane == 0) TRACE(1, 21);
-                    if (l + 1 < L) open_layer(l + 1, t >= dn);          // prev(l+1) in the shadow of the gate epilogue
+                    if (l > 0) skip_layer(l - 1, nullptr);              // in the shadow of the gate epilogue
                     dw = wait_stage();                                  // Wres_l
                     wait_epi();                                         // h tile ready, D1 consumed
                     if (lane == 0) TRACE(1, 22);
                     mma4(d_h + (uint64_t)(l & 1) * TILE_D, dw, d1, idesc64, false, dx_full, &w_empty[stage]);   // Dx = Wres . h
                     advance();
                     if (lane == 0) TRACE(1, 23);
-                    skip_layer(l, l == L - 1 ? skip_full : nullptr);    // in the shadow of the residual epilogue
+                    if (l + 1 < L) open_layer(l + 1, t >= dn);          // in the shadow of the residual epilogue
                     if (lane == 0) TRACE(1, 24);
                     d = dn;
                 }
+                skip_layer(L - 1, skip_full);
                 wait_epi();                                             // relu(skip) tile ready
                 for (int kt = 0; kt < S / 64; kt++)
                     for (int nh = 0; nh < 2; nh++) {
@@ -547,7 +533,6 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             const bool dump = p.dump && (t == t_end - 1);
             const float sel = valid ? __ldg(p.sel + (size_t)t * B + b) : 0.5f;
             prestore(0);                                                // D1[0] <- Lh[t][0] + Bh (Dza of the previous sample is consumed)
-            bool pre1_pending = L > 1;                                  // D1[1] is initialised right after x_0 is published
             // ---------------- embedding: x0 = tanh(embPrev[yPrev] + embCur[yCur])   (reference.cpp:42-57)
             if (wv) {
                 const uint4* ep = reinterpret_cast<const uint4*>(embPrev + (size_t)yp * R + c32);
@@ -571,7 +556,6 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             }
             publish();                                                  // x_0 ready
             if (tid == 0) TRACE(0, 1);
-            if (pre1_pending) prestore(1);
             if (wv) store_history(ring_tile(t, 0));
 
             for (int l = 0; l < L; l++) {
@@ -600,21 +584,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     for (int q = 0; q < CQ; q++) st_tile(th, q4 + q, make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]));
                 }
                 if (tid == 0) TRACE(0, 12);
-                if (dump && l > 0 && wv) {
-                    // skip(l-1) was issued before cur(l), so d1_full(l) covers it, and skip(l) waits for the arrival below:
-                    // the skip sum holds layers 0..l-1 exactly now
-                    const int c_lo = sub * (S / NS);
-                    for (int c0 = c_lo; c0 < c_lo + S / NS; c0 += 16) {
-                        uint32_t w[16];
-                        tmem_ld16(DSKIP + lane_off + c0, w);
-                        tmem_ld_wait();
-                        if (valid)
-                            for (int j = 0; j < 16; j++)
-                                p.skipOut[((size_t)(l - 1) * B + b) * S + c0 + j] = __uint_as_float(w[j]) + gbias[im.b_bskp + (size_t)(l - 1) * S + c0 + j];
-                    }
-                }
                 publish();                                              // h ready, D1 drained
                 if (tid == 0) TRACE(0, 3);
+                if (l + 1 < L) prestore(l + 1);                         // while the residual GEMM runs
                 // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
                 mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
                 tc_fence_after_sync();
@@ -642,12 +614,24 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 #pragma unroll
                             for (int j = 0; j < CW; j++) p.xtOut[((size_t)l * B + b) * R + c32 + j] = x[j];
                         }
+                        // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
+                        // next contribution is only issued after the arrival below: no extra barrier needed
+                        if (l > 0) {
+                            const int c_lo = sub * (S / NS);
+                            for (int c0 = c_lo; c0 < c_lo + S / NS; c0 += 16) {
+                                uint32_t w[16];
+                                tmem_ld16(DSKIP + lane_off + c0, w);
+                                tmem_ld_wait();
+                                if (valid)
+                                    for (int j = 0; j < 16; j++)
+                                        p.skipOut[((size_t)(l - 1) * B + b) * S + c0 + j] = __uint_as_float(w[j]) + gbias[im.b_bskp + (size_t)(l - 1) * S + c0 + j];
+                            }
+                        }
                     }
                 }
                 if (l + 1 < L) {
                     publish();                                          // x_{l+1} ready
                     if (tid == 0) TRACE(0, 5);
-                    if (l + 2 < L) prestore(l + 2);                     // the buffer Dx was just read from becomes D1 of layer l+2
                     if (wv) store_history(ring_tile(t, l + 1));
                 }
             }
