@@ -20,6 +20,8 @@
 #include "wn_math.cuh"
 #include "wn_sm100.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 using namespace sm100;
@@ -58,14 +60,16 @@ __host__ __device__ inline size_t tc_smem_bytes(int S, int L, int nstage)
 // Conditioning in the tensor-core layout: fp16 [N][L][Bpad rows][2 halves of 64 channels], tiled per 128 utterances;
 // inside a tile: [half][row][128 B], 16-byte chunks XOR-swizzled with (row & 7) -- i.e. exactly the K-major
 // SWIZZLE_128B image of an MMA A-operand tile, so a 1-D bulk TMA copy of rows*128 bytes needs no further shuffling.
-__host__ __device__ inline int cond_rows(int B, int tile) { const int r = B - tile * 128; return r >= 128 ? 128 : ((r + 7) & ~7); }
-__host__ __device__ inline size_t cond_bpad(int B) { const int nt = (B + 127) / 128; return (size_t)(nt - 1) * 128 + cond_rows(B, nt - 1); }
+// TU = utterances per tile: 64 (four threads per utterance, the lower-latency variant) while the batch fits the SMs
+// that way, 128 otherwise.
+__host__ __device__ inline int cond_rows(int B, int tile, int TU) { const int r = B - tile * TU; return r >= TU ? TU : ((r + 7) & ~7); }
+__host__ __device__ inline size_t cond_bpad(int B, int TU) { const int nt = (B + TU - 1) / TU; return (size_t)(nt - 1) * TU + cond_rows(B, nt - 1, TU); }
 
-__global__ void tc_cond_kernel(unsigned char* __restrict__ dst, const float* __restrict__ src, int first_sample, int nsamples, int L, int B)
+__global__ void tc_cond_kernel(unsigned char* __restrict__ dst, const float* __restrict__ src, int first_sample, int nsamples, int L, int B, int TU)
 {
     // one thread per (sample, layer, utterance, 8-channel chunk): 32 B in, 16 B out
     const size_t total = (size_t)nsamples * L * B * 16;
-    const size_t bpad = cond_bpad(B);
+    const size_t bpad = cond_bpad(B, TU);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i & 15);
         const size_t rowi = i >> 4;                       // (s * L + l) * B + b
@@ -77,8 +81,8 @@ __global__ void tc_cond_kernel(unsigned char* __restrict__ dst, const float* __r
         uint4 o;
         o.x = *reinterpret_cast<unsigned*>(&h0); o.y = *reinterpret_cast<unsigned*>(&h1);
         o.z = *reinterpret_cast<unsigned*>(&h2); o.w = *reinterpret_cast<unsigned*>(&h3);
-        const int tile = b >> 7, r = b & 127, half = c >> 3, q = c & 7;
-        const size_t off = (((size_t)first_sample * L + sl) * bpad + (size_t)tile * 128) * 256 + (size_t)half * cond_rows(B, tile) * 128 +
+        const int tile = b / TU, r = b % TU, half = c >> 3, q = c & 7;
+        const size_t off = (((size_t)first_sample * L + sl) * bpad + (size_t)tile * TU) * 256 + (size_t)half * cond_rows(B, tile, TU) * 128 +
                            (size_t)r * 128 + (size_t)((q ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(dst + off) = o;
     }
@@ -230,12 +234,13 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     const uint32_t D1B = tmem_base, DSKIP = tmem_base + 256, DZS = tmem_base + 256, DZA = tmem_base;
 
     // conditioning tile geometry (see tc_cond_kernel)
-    const int c_rows = cond_rows(B, tile);
+    constexpr int TU = DUP ? 64 : 128;              // utterances per tile
+    const int c_rows = cond_rows(B, tile, TU);
     const uint32_t c_bytes = (uint32_t)c_rows * 128u;
-    const size_t c_bpad = cond_bpad(B);
+    const size_t c_bpad = cond_bpad(B, TU);
     const unsigned char* gcond = static_cast<const unsigned char*>(p.Lh);
     auto cond_ptr = [&](int t, int l, int half) -> const unsigned char* {
-        return gcond + (((size_t)t * L + l) * c_bpad + (size_t)tile * 128) * 256 + (size_t)half * c_bytes;
+        return gcond + (((size_t)t * L + l) * c_bpad + (size_t)tile * TU) * 256 + (size_t)half * c_bytes;
     };
 
     // debug timeline: role r (0 epilogue thread 0, 1 MMA issuer, 2 producer) appends (tag << 48 | clock) words
@@ -425,9 +430,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         const int row = quad * 32 + lane;               // TMEM lane / tile row this thread reads
         const int u = DUP ? (row & 63) : row;           // utterance of the tile
         const int sub = DUP ? (ch * 2 + (row >> 6)) : ch;   // which CW-wide slice of the channels is mine
-        const int b = tile * 128 + u;
+        const int b = tile * TU + u;
         const bool valid = b < B;
-        const bool wv = tile * 128 + (DUP ? (quad & 1) : quad) * 32 < B;   // warp has a live utterance: dead warps only keep
+        const bool wv = tile * TU + (DUP ? (quad & 1) : quad) * 32 < B;   // warp has a live utterance: dead warps only keep
                                                         // the barrier protocol going (their rows are never read back)
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const int c32 = CW * sub, q4 = CQ * sub;        // first channel / first chunk of this thread
@@ -802,9 +807,20 @@ bool wn_tc_supported(int R_, int S, int A_, int L, int)
 
 size_t wn_tc_image_bytes(int, int S, int, int L) { return tc_image(S, L).total; }
 
-size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B) { return (size_t)(maxDil + 1) * L * ((B + 127) / 128) * TILE; }
+// 64-utterance tiles (the lower-latency four-threads-per-utterance variant) as long as one wave of CTAs covers the batch
+int wn_tc_tile_utt(int B)
+{
+    if (getenv("NVWN_TC_NODUP")) return 128;
+    return B <= 64 * 148 ? 64 : 128;
+}
 
-size_t wn_tc_cond_bytes(int L, int B, int N) { return (size_t)N * L * cond_bpad(B) * 256; }
+size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B)
+{
+    const int TU = wn_tc_tile_utt(B);
+    return (size_t)(maxDil + 1) * L * ((B + TU - 1) / TU) * TILE;
+}
+
+size_t wn_tc_cond_bytes(int L, int B, int N) { return (size_t)N * L * cond_bpad(B, wn_tc_tile_utt(B)) * 256; }
 
 cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream)
 {
@@ -812,7 +828,7 @@ cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample
     const size_t total = (size_t)nsamples * L * B * 16;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    tc_cond_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<unsigned char*>(dst), src_dev, first_sample, nsamples, L, B);
+    tc_cond_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<unsigned char*>(dst), src_dev, first_sample, nsamples, L, B, wn_tc_tile_utt(B));
     return cudaGetLastError();
 }
 
@@ -830,9 +846,10 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t 
     const int nstage = pick_nstage(p.S, p.L);
     if (nstage < 3) return cudaErrorInvalidValue;
     const size_t smem = tc_smem_bytes(p.S, p.L, nstage);
-    const int grid = (p.B + 127) / 128;
+    const int TU = wn_tc_tile_utt(p.B);
+    const int grid = (p.B + TU - 1) / TU;
     cudaError_t e = cudaErrorInvalidValue;
-    const bool dup = p.B <= 64 && !getenv("NVWN_TC_NODUP");    // single tile with at most 64 utterances: 4 threads per utterance
+    const bool dup = TU == 64;                                  // tiles of at most 64 utterances: 4 threads per utterance
     const unsigned char* im8 = static_cast<const unsigned char*>(tc_image_);
 #define WN_TC_LAUNCH(SV, DV)                                                                                         \
     do {                                                                                                             \
