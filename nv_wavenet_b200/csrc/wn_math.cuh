@@ -89,6 +89,13 @@ __device__ __forceinline__ float sigmoidf_fast(float x)
     // sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 : one MUFU instead of ex2 + rcp
     return fmaf(0.5f, tanhf_fast(0.5f * x), 0.5f);
 }
+// two fp16 tanh for one MUFU issue slot
+__device__ __forceinline__ __half2 tanh_h2(__half2 x)
+{
+    uint32_t y, xi = *reinterpret_cast<const uint32_t*>(&x);
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(xi));
+    return *reinterpret_cast<const __half2*>(&y);
+}
 __device__ __forceinline__ float exp2f_fast(float x)
 {
     float y;

@@ -33,12 +33,14 @@ constexpr int NEPI = 256;
 
 struct TcImage {                            // byte offsets inside the packed image
     size_t layer_bytes, off_out, off_bias, total;
-    size_t b_bh, b_bres, b_bskp, b_bzs, b_bza;     // float offsets inside the bias block
+    size_t b_bh, b_bres, b_bskp, b_bzs, b_bza, b_bhf;     // float offsets inside the bias block
+    size_t l_wf;                                   // byte offset of the folded matrix Wcur_l . Wres_{l-1} inside a layer block
 };
 __host__ __device__ inline TcImage tc_image(int S, int L)
 {
     TcImage im;
-    im.layer_bytes = (size_t)TILE * 2 + TILE / 2 + (size_t)(S / 128) * TILE;
+    im.l_wf = (size_t)TILE * 2 + TILE / 2 + (size_t)(S / 128) * TILE;
+    im.layer_bytes = im.l_wf + TILE;
     im.off_out = (size_t)L * im.layer_bytes;
     im.off_bias = im.off_out + (size_t)(S / 64) * 2 * TILE + (size_t)(A / 64) * 2 * TILE;
     im.b_bh = 0;
@@ -46,7 +48,8 @@ __host__ __device__ inline TcImage tc_image(int S, int L)
     im.b_bskp = im.b_bres + (size_t)L * 64;
     im.b_bzs = im.b_bskp + (size_t)L * S;
     im.b_bza = im.b_bzs + A;
-    im.total = im.off_bias + (im.b_bza + A) * sizeof(float);
+    im.b_bhf = im.b_bza + A;
+    im.total = im.off_bias + (im.b_bhf + (size_t)L * 128) * sizeof(float);
     return im;
 }
 
@@ -114,6 +117,16 @@ __global__ void tc_pack_kernel(WnParams p, unsigned char* __restrict__ img, TcIm
         const int l = (int)(i / ((size_t)S * 64)), s = (int)((i / 64) % S), k = (int)(i % 64);
         put((size_t)l * im.layer_bytes + 2 * TILE + TILE / 2 + (size_t)(s / 128) * TILE, s % 128, k, Wskip[(size_t)l * S * 64 + s + (size_t)k * S]);
     }
+    // folded matrix of the fused schedule: Wf_l = Wcur_l . Wres_{l-1} (fp32 accumulation of the fp16 factors, one rounding),
+    // so that Wcur_l . x_l = Wcur_l . x_{l-1} + Wf_l . h_{l-1} + Wcur_l . Bres_{l-1}
+    for (size_t i = g0; i < (size_t)L * 128 * 64; i += gstride) {
+        const int l = (int)(i / (128 * 64)), c = (int)(i % (128 * 64)) / 64, k = (int)(i % 64);
+        if (l == 0) continue;
+        float acc = 0.f;
+        for (int j = 0; j < 64; j++)
+            acc = fmaf(__half2float(Wcur[(size_t)l * 128 * 64 + c + (size_t)j * 128]), __half2float(Wres[(size_t)(l - 1) * 64 * 64 + j + (size_t)k * 64]), acc);
+        put((size_t)l * im.layer_bytes + im.l_wf, c, k, __float2half_rn(acc));
+    }
     // output layers: chunk (kt, nh) = rows a in [128 nh, +128), k in [64 kt, +64)
     for (size_t i = g0; i < (size_t)A * S; i += gstride) {
         const int a = (int)(i / S), s = (int)(i % S);
@@ -129,7 +142,16 @@ __global__ void tc_pack_kernel(WnParams p, unsigned char* __restrict__ img, TcIm
     const __half* Bh = static_cast<const __half*>(p.Bh);
     const __half* Bres = static_cast<const __half*>(p.Bres);
     const __half* Bskip = static_cast<const __half*>(p.Bskip);
-    for (size_t i = g0; i < (size_t)L * 128; i += gstride) bias[im.b_bh + i] = __half2float(Bh[i]);
+    for (size_t i = g0; i < (size_t)L * 128; i += gstride) {
+        const int l = (int)(i / 128), c = (int)(i % 128);
+        const float bh = __half2float(Bh[i]);
+        bias[im.b_bh + i] = bh;
+        float acc = 0.f;                                        // Wcur_l . Bres_{l-1}
+        if (l > 0)
+            for (int j = 0; j < 64; j++)
+                acc = fmaf(__half2float(Wcur[(size_t)l * 128 * 64 + c + (size_t)j * 128]), __half2float(Bres[(size_t)(l - 1) * 64 + j]), acc);
+        bias[im.b_bhf + i] = bh + acc;
+    }
     for (size_t i = g0; i < (size_t)L * 64; i += gstride) bias[im.b_bres + i] = __half2float(Bres[i]);
     for (size_t s = g0; s < (size_t)S; s += gstride) {
         float acc = 0.f;
@@ -157,7 +179,13 @@ __device__ __forceinline__ uint32_t chunk_off(int row, int q) { return (uint32_t
 // DUP (tiles with <= 64 live utterances, e.g. the 64-per-GPU headline case): every utterance occupies TWO rows (u and u+64)
 // of each activation tile / TMEM accumulator, so that all four TMEM lane quadrants -- and with them all four warp
 // schedulers and their MUFU pipes -- work for it: 4 threads per utterance instead of 2, each on 16 of the 64 channels.
-template <int S, bool DUP>
+//
+// FUSED (default schedule): ONE MMA <-> epilogue round trip per layer instead of two.  The pre-activation of layer l is
+// accumulated as  (Lh + Bh') [tcgen05.st] + Wprev_l.x_l[t-d] + Wcur_l.x_{l-1} [both in the background, one layer early]
+// + Wf_l.h_{l-1} [the only GEMM on the critical path], Wf_l = Wcur_l.Wres_{l-1} folded at pack time.  The residual GEMM
+// Wres_{l-1}.h_{l-1} still produces x_l (history ring, next layer's background GEMM, dump) but nothing waits on it
+// before the next gate.
+template <int S, bool DUP, bool FUSED>
 __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const unsigned char* __restrict__ img, const int nstage)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -168,6 +196,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     const TcImage im = tc_image(S, L);
 
     unsigned char* t_xc = smem;                    // x tile of the current layer        (= BIG k-tile 0)
+    unsigned char* t_x1 = smem + 3 * TILE;         // FUSED: x tiles ping-pong by layer parity (t_xc, t_x1 = BIG k-tile 3)
     unsigned char* t_h = smem + TILE;              // gated activation tiles, double buffered by layer parity (= BIG k-tiles 1, 2)
     unsigned char* t_big = smem;                   // [128 x 256] as 4 k-tiles: relu(skip), relu(Zs), then fp16 logits scratch
     unsigned char* ring = smem + 4 * TILE;
@@ -219,7 +248,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     if (warp == 8) tmem_alloc<512>(tmem_slot);
     {   // biases and the identity tile -> shared memory
         const float* gb = reinterpret_cast<const float*>(img + im.off_bias);
-        for (int i = tid; i < L * 128; i += NT) s_bh[i] = gb[im.b_bh + i];
+        for (int i = tid; i < L * 128; i += NT) s_bh[i] = gb[(FUSED ? im.b_bhf : im.b_bh) + i];
         for (int i = tid; i < L * 64; i += NT) s_bres[i] = gb[im.b_bres + i];
         for (int i = tid; i < S; i += NT) s_bsk[i] = gb[im.b_bskp + (size_t)(L - 1) * S + i];
         for (int i = tid; i < A; i += NT) { s_bzs[i] = gb[im.b_bzs + i]; s_bza[i] = gb[im.b_bza + i]; }
@@ -246,7 +275,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     // debug timeline: role r (0 epilogue thread 0, 1 MMA issuer, 2 producer) appends (tag << 48 | clock) words
     unsigned long long* trc = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
     int trn = 0;
-#define TRACE(role, tag) do { if (trc && t == p.trace_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
+    const int tr_t = p.trace_t & 0xFFFF, tr_tid = p.trace_t >> 16;     // sample and epilogue thread to trace
+#define TRACE(role, tag) do { if (trc && t == tr_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
 
     if (warp == 8) {
         // =============================================================== TMA producer (whole warp converged, one lane issues)
@@ -298,6 +328,41 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             auto put_skip = [&](int l) {
                 for (int c = 0; c < S / 128; c++) put(img + (size_t)l * im.layer_bytes + 2 * TILE + TILE / 2 + (size_t)c * TILE, TILE);
             };
+            if (FUSED) {
+                // chunk order of the fused schedule (see the MMA issuer):
+                //   prev(0) cur(0) prev(1) cur(1) | res(0) Wf(1) skip(0) prev(2) cur(2) | ... | res(L-2) Wf(L-1) skip(L-2) | skip(L-1) | Wzs | Wza
+                // (on the dumping sample skip(l-1) precedes Wf(l), and res(L-1) is computed as well)
+                for (int t = t_begin; t < t_end; t++) {
+                    const bool dstep = p.dump && (t == t_end - 1);
+                    put_cond(t, 0);
+                    put_prev(t, 0, 1);
+                    put(img + TILE, TILE);                              // Wcur_0
+                    if (L > 1) {
+                        put_cond(t, 1);
+                        put_prev(t, 1, s_dil[1]);
+                        put(img + im.layer_bytes + TILE, TILE);         // Wcur_1
+                    }
+                    for (int l = 1; l < L; l++) {
+                        const unsigned char* lw = img + (size_t)l * im.layer_bytes;
+                        if (lane == 0) TRACE(2, 100 + l);
+                        if (NC == 2 && l + 1 < L) put_cond(t, l + 1);
+                        put(lw - im.layer_bytes + 2 * TILE, TILE / 2);  // Wres_{l-1}
+                        if (dstep) put_skip(l - 1);
+                        put(lw + im.l_wf, TILE);                        // Wf_l
+                        if (!dstep) put_skip(l - 1);
+                        if (l + 1 < L) {
+                            // single conditioning buffer: its consumer (gate l) first needs the residual of layer l-1 above
+                            if (NC == 1) put_cond(t, l + 1);
+                            put_prev(t, l + 1, s_dil[l + 1]);
+                            put(lw + im.layer_bytes + TILE, TILE);      // Wcur_{l+1}
+                        }
+                    }
+                    if (dstep) put(img + (size_t)(L - 1) * im.layer_bytes + 2 * TILE, TILE / 2);
+                    put_skip(L - 1);
+                    const unsigned char* ow = img + im.off_out;
+                    for (int c = 0; c < (S / 64) * 2 + (A / 64) * 2; c++) put(ow + (size_t)c * TILE, TILE);
+                }
+            } else
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;
                 put_cond(t, 0);
@@ -359,6 +424,20 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     advance();
                 }
             };
+            // fused schedule: the conditioning and the bias are added by the gate itself, so the FIRST GEMM into an
+            // accumulator overwrites it: Wprev_l . x[t-d] if the history reaches back that far, else the Wcur GEMM
+            auto open_f = [&](int l, bool has_prev, bool wait_x) {
+                if (wait_x) { mbar_wait(pre_done, ph_pre); ph_pre ^= 1; tc_fence_after_sync(); }
+                if (has_prev) {
+                    const uint64_t da = wait_stage();
+                    const int sa = stage;
+                    advance();
+                    const uint64_t db = wait_stage();
+                    tc_fence_after_sync();
+                    mma4(da, db, D1B + (uint32_t)(l & 1) * 128, idesc128, false, &w_empty[sa], &w_empty[stage]);
+                    advance();
+                }
+            };
             // skip(l): Dskip (+)= Wskip_l . h_l, h_l in the H buffer of parity l
             auto skip_layer = [&](int l, uint64_t* done_bar) {
                 const uint64_t dh = d_h + (uint64_t)(l & 1) * TILE_D;
@@ -372,6 +451,112 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             // Issue order per layer: cur(l) | skip(l-1) in the shadow of the gate epilogue | res(l) | prev(l+1) in the shadow
             // of the residual epilogue.  Nothing but cur / res sits between an epilogue arrival and the accumulator it
             // waits for.
+            auto out_gemms = [&]() {
+                wait_epi();                                             // relu(skip) tile ready
+                for (int kt = 0; kt < S / 64; kt++)
+                    for (int nh = 0; nh < 2; nh++) {
+                        const uint64_t dw = wait_stage();
+                        tc_fence_after_sync();
+                        const bool last = (kt == S / 64 - 1) && nh == 1;
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
+                        advance();
+                    }
+                wait_epi();                                             // relu(Zs) tile ready
+                for (int kt = 0; kt < A / 64; kt++)
+                    for (int nh = 0; nh < 2; nh++) {
+                        const uint64_t dw = wait_stage();
+                        tc_fence_after_sync();
+                        const bool last = (kt == A / 64 - 1) && nh == 1;
+                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
+                        advance();
+                    }
+            };
+            if (FUSED) {
+                // Per gate h_{l-1}: res(l-1) [-> x_l, off the critical path] | Wf(l) -> commit d1_full (the only GEMM the next
+                // gate waits for) | skip(l-1) | then, once the epilogue has initialised D1 of layer l+1: prev(l+1) and
+                // Wcur_{l+1}.x_l in the background.
+                const uint64_t d_x[2] = {d_xc, d_big + 3 * TILE_D};
+                // History ring: the published x_l tile goes shared -> global as ONE bulk copy issued here (async proxy on both
+                // ends: no generic-proxy stores + proxy fences in 256 epilogue threads).  Lane 0 owns the bulk group; it
+                // waits for completion one layer later, before the commits that (through the weight ring) let the producer
+                // run ahead to the loads of the next sample, and before the tile is overwritten.
+                const uint32_t hist_bytes = (uint32_t)(DUP ? TILE / 2 : TILE);
+                auto hist_store = [&](int t, int l) {
+                    if (lane == 0) tma_store_1d(ring_tile(t, l), (l & 1) ? t_x1 : t_xc, hist_bytes);
+                    __syncwarp();
+                };
+                auto hist_wait = [&]() { if (lane == 0) tma_store_wait_all(); __syncwarp(); };
+                for (int t = t_begin; t < t_end; t++) {
+                    const bool dstep = p.dump && (t == t_end - 1);
+                    uint64_t dw;
+                    wait_epi();                                         // x_0 tile ready (and Dza of the previous sample consumed)
+                    hist_store(t, 0);
+                    if (lane == 0) TRACE(1, 20);
+                    open_f(0, t >= 1, false);
+                    dw = wait_stage();
+                    tc_fence_after_sync();
+                    mma4(d_x[0], dw, D1B, idesc128, t >= 1, d1_full, &w_empty[stage]);      // D1[0] (+)= Wcur_0 . x_0
+                    advance();
+                    if (L > 1) {
+                        open_f(1, t >= s_dil[1], false);
+                        dw = wait_stage();
+                        tc_fence_after_sync();
+                        mma4(d_x[0], dw, D1B + 128, idesc128, t >= s_dil[1], nullptr, &w_empty[stage]);   // D1[1] (+)= Wcur_1 . x_0
+                        advance();
+                    }
+                    for (int l = 1; l < L; l++) {
+                        const uint64_t dh = d_h + (uint64_t)((l - 1) & 1) * TILE_D;
+                        dw = wait_stage();                              // Wres_{l-1} already landed when h arrives
+                        wait_epi();                                     // h_{l-1} ready, D1[(l-1)&1] drained
+                        if (lane == 0) TRACE(1, 22);
+                        hist_wait();
+                        if (lane == 0) TRACE(1, 28);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) umma_f16(D1B + (uint32_t)((l - 1) & 1) * 128, dh + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc64, k ? 1u : 0u);
+                        }
+                        __syncwarp();
+                        if (lane == 0) TRACE(1, 26);
+                        if (elect_one()) { umma_commit(dx_full); umma_commit(&w_empty[stage]); }
+                        __syncwarp();
+                        advance();
+                        if (lane == 0) TRACE(1, 25);
+                        if (dstep) skip_layer(l - 1, nullptr);
+                        dw = wait_stage();
+                        tc_fence_after_sync();
+                        if (lane == 0) TRACE(1, 29);
+                        mma4(dh, dw, D1B + (uint32_t)(l & 1) * 128, idesc128, true, d1_full, &w_empty[stage]);         // D1[l] += Wf_l . h
+                        advance();
+                        if (lane == 0) TRACE(1, 21);
+                        if (!dstep) skip_layer(l - 1, nullptr);
+                        if (lane == 0) TRACE(1, 23);
+                        if (l + 1 < L) {
+                            open_f(l + 1, t >= s_dil[l + 1], true);     // waits: x_l tile published, Dx of layer l-1 consumed
+                            if (lane == 0) TRACE(1, 32);
+                            dw = wait_stage();
+                            tc_fence_after_sync();
+                            if (lane == 0) TRACE(1, 33);
+                            mma4(d_x[l & 1], dw, D1B + (uint32_t)((l + 1) & 1) * 128, idesc128, t >= s_dil[l + 1], nullptr, &w_empty[stage]);   // (+)= Wcur_{l+1} . x_l
+                            advance();
+                        } else {
+                            mbar_wait(pre_done, ph_pre); ph_pre ^= 1;   // x_{L-1} tile published (history only)
+                        }
+                        if (lane == 0) TRACE(1, 34);
+                        hist_store(t, l);
+                        if (lane == 0) TRACE(1, 24);
+                    }
+                    wait_epi();                                         // h_{L-1}
+                    hist_wait();
+                    if (dstep) {
+                        dw = wait_stage();
+                        tc_fence_after_sync();
+                        mma4(d_h + (uint64_t)((L - 1) & 1) * TILE_D, dw, D1B + (uint32_t)((L - 1) & 1) * 128, idesc64, false, dx_full, &w_empty[stage]);
+                        advance();
+                    }
+                    skip_layer(L - 1, skip_full);
+                    out_gemms();
+                }
+            } else
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
                 for (int l = 0; l < L; l++) {
@@ -398,24 +583,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     d = dn;
                 }
                 skip_layer(L - 1, skip_full);
-                wait_epi();                                             // relu(skip) tile ready
-                for (int kt = 0; kt < S / 64; kt++)
-                    for (int nh = 0; nh < 2; nh++) {
-                        const uint64_t dw = wait_stage();
-                        tc_fence_after_sync();
-                        const bool last = (kt == S / 64 - 1) && nh == 1;
-                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZS + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
-                        advance();
-                    }
-                wait_epi();                                             // relu(Zs) tile ready
-                for (int kt = 0; kt < A / 64; kt++)
-                    for (int nh = 0; nh < 2; nh++) {
-                        const uint64_t dw = wait_stage();
-                        tc_fence_after_sync();
-                        const bool last = (kt == A / 64 - 1) && nh == 1;
-                        mma4(d_big + (uint64_t)kt * TILE_D, dw, DZA + nh * 128, idesc128, kt > 0, &w_empty[stage], last ? out_full : nullptr);
-                        advance();
-                    }
+                out_gemms();
             }
         }
     } else {
@@ -481,19 +649,23 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         // conditioning buffer: tcgen05.st, done while this thread would otherwise wait for the residual GEMM.  Each row
         // needs all 128 columns from the two threads that may touch its TMEM lane: channel half `ch`, both gate halves.
         int g_pre = 0;
+        bool tr_on = false;
         auto prestore = [&](int ln) {
             const int cbuf = g_pre % NC;
             mbar_wait(&cond_full[cbuf], (g_pre / NC) & 1);
+            if (tid == tr_tid && trc && tr_on && trn < 1023) trc[trn++] = (14ull << 48) | (clock64() & 0xFFFFFFFFFFFFull);
             if (wv) {
                 const unsigned char* cb = t_cond + (size_t)cbuf * CB;
                 const uint32_t d1n = D1B + (uint32_t)(ln & 1) * 128 + lane_off;
+                // only the columns the gate thread of THIS row reads: [c32, c32 + CW) of both gate halves (with DUP the other
+                // columns of the row belong to the twin row's thread and are never read from this one)
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
-                    const float* bh = s_bh + (size_t)ln * 128 + 64 * half + 32 * ch;
-                    uint32_t v[32];
+                    const float* bh = s_bh + (size_t)ln * 128 + 64 * half + c32;
+                    uint32_t v[CW];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint4 w = *reinterpret_cast<const uint4*>(cb + (size_t)half * c_bytes + chunk_off(u, 4 * ch + q));
+                    for (int q = 0; q < CQ; q++) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(cb + (size_t)half * c_bytes + chunk_off(u, q4 + q));
                         const uint32_t wv4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
@@ -502,10 +674,12 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                             v[8 * q + 2 * j + 1] = __float_as_uint(f.y + bh[8 * q + 2 * j + 1]);
                         }
                     }
-                    tmem_st32(d1n + 64 * half + 32 * ch, v);
+                    if constexpr (CW == 32) tmem_st32(d1n + 64 * half + c32, v);
+                    else tmem_st16(d1n + 64 * half + c32, v);
                 }
                 tmem_st_wait();
             }
+            if (tid == tr_tid && trc && tr_on && trn < 1023) trc[trn++] = (15ull << 48) | (clock64() & 0xFFFFFFFFFFFFull);
             tc_fence_before_sync();
             mbar_arrive(&cond_empty[cbuf]);
             mbar_arrive(pre_done);
@@ -536,8 +710,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 
         for (int t = t_begin; t < t_end; t++) {
             const bool dump = p.dump && (t == t_end - 1);
+            tr_on = (t == tr_t);
             const float sel = valid ? __ldg(p.sel + (size_t)t * B + b) : 0.5f;
-            prestore(0);                                                // D1[0] <- Lh[t][0] + Bh (Dza of the previous sample is consumed)
+            if (!FUSED) prestore(0);                                    // D1[0] <- Lh[t][0] + Bh (Dza of the previous sample is consumed)
             // ---------------- embedding: x0 = tanh(embPrev[yPrev] + embCur[yCur])   (reference.cpp:42-57)
             if (wv) {
                 const uint4* ep = reinterpret_cast<const uint4*>(embPrev + (size_t)yp * R + c32);
@@ -560,83 +735,159 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 }
             }
             publish();                                                  // x_0 ready
-            if (tid == 0) TRACE(0, 1);
-            if (wv) store_history(ring_tile(t, 0));
+            if (tid == tr_tid) TRACE(0, 1);
+            if (!FUSED && wv) store_history(ring_tile(t, 0));
 
-            for (int l = 0; l < L; l++) {
-                const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128 + lane_off;
-                unsigned char* th = t_h + (size_t)(l & 1) * TILE;
-                // ---------------- gate: h = tanh(a[0:R]) * sigmoid(a[R:2R]); D1 already holds the complete pre-activation
-                // a = (Lh[t][l] + Bh) + Wprev.x[t-d] + Wcur.x[t]   (reference.cpp:67-80)
-                mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
-                tc_fence_after_sync();
-                if (tid == 0) TRACE(0, 2);
+            // fused schedule: Lh[t][l] + Bh' of this thread's channels from the TMA-fed conditioning buffer -> registers
+            // (done BEFORE waiting for the accumulator)
+            float cnd[2 * CW];
+            auto load_cond = [&](int ln) {
+                const int cbuf = g_pre % NC;
+                mbar_wait(&cond_full[cbuf], (g_pre / NC) & 1);
+                if (tid == tr_tid) TRACE(0, 14);
                 if (wv) {
-                    uint32_t ta[32], sa[32];
-                    tmem_ldc(d1 + c32, ta);
-                    tmem_ldc(d1 + 64 + c32, sa);
-                    tmem_ld_wait();
-                    uint32_t hp[CW / 2];
+                    const unsigned char* cb = t_cond + (size_t)cbuf * CB;
 #pragma unroll
-                    for (int j = 0; j < CW; j += 2) {
-                        const float a0 = __uint_as_float(ta[j]), a1 = __uint_as_float(ta[j + 1]);
-                        const float g0 = __uint_as_float(sa[j]), g1 = __uint_as_float(sa[j + 1]);
-                        const float h0 = wn::tanhf_fast(a0) * wn::sigmoidf_fast(g0);
-                        const float h1 = wn::tanhf_fast(a1) * wn::sigmoidf_fast(g1);
-                        hp[j >> 1] = pack_h2(h0, h1);
-                    }
+                    for (int half = 0; half < 2; half++) {
+                        const float* bh = s_bh + (size_t)ln * 128 + 64 * half + c32;
 #pragma unroll
-                    for (int q = 0; q < CQ; q++) st_tile(th, q4 + q, make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]));
-                }
-                if (tid == 0) TRACE(0, 12);
-                publish();                                              // h ready, D1 drained
-                if (tid == 0) TRACE(0, 3);
-                if (l + 1 < L) prestore(l + 1);                         // while the residual GEMM runs
-                // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
-                mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
-                tc_fence_after_sync();
-                if (tid == 0) TRACE(0, 4);
-                if (wv) {
-                    const float* br = s_bres + (size_t)l * 64 + c32;
-                    uint32_t v[32];
-                    tmem_ldc(d1 + c32, v);
-                    tmem_ld_wait();
-                    uint32_t o[CW / 2];
+                        for (int q = 0; q < CQ; q++) {
+                            const uint4 w = *reinterpret_cast<const uint4*>(cb + (size_t)half * c_bytes + chunk_off(u, q4 + q));
+                            const uint32_t wv4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int j = 0; j < CW; j += 2) {
-                        const float2 bb = *reinterpret_cast<const float2*>(br + j);
-                        float v0 = x[j] + (__uint_as_float(v[j]) + bb.x), v1 = x[j + 1] + (__uint_as_float(v[j + 1]) + bb.y);
-                        if (!valid) { v0 = 0.f; v1 = 0.f; }
-                        x[j] = v0; x[j + 1] = v1;
-                        o[j >> 1] = pack_h2(v0, v1);
-                    }
-                    if (l + 1 < L) {
-#pragma unroll
-                        for (int q = 0; q < CQ; q++) st_tile(t_xc, q4 + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
-                    }
-                    if (dump) {                                         // last sample of a dumping launch only
-                        if (valid) {
-#pragma unroll
-                            for (int j = 0; j < CW; j++) p.xtOut[((size_t)l * B + b) * R + c32 + j] = x[j];
-                        }
-                        // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
-                        // next contribution is only issued after the arrival below: no extra barrier needed
-                        if (l > 0) {
-                            const int c_lo = sub * (S / NS);
-                            for (int c0 = c_lo; c0 < c_lo + S / NS; c0 += 16) {
-                                uint32_t w[16];
-                                tmem_ld16(DSKIP + lane_off + c0, w);
-                                tmem_ld_wait();
-                                if (valid)
-                                    for (int j = 0; j < 16; j++)
-                                        p.skipOut[((size_t)(l - 1) * B + b) * S + c0 + j] = __uint_as_float(w[j]) + gbias[im.b_bskp + (size_t)(l - 1) * S + c0 + j];
+                            for (int j = 0; j < 4; j++) {
+                                const float2 f = unpack_h2(wv4[j]);
+                                cnd[half * CW + 8 * q + 2 * j] = f.x + bh[8 * q + 2 * j];
+                                cnd[half * CW + 8 * q + 2 * j + 1] = f.y + bh[8 * q + 2 * j + 1];
                             }
                         }
                     }
                 }
+                mbar_arrive(&cond_empty[cbuf]);
+                g_pre++;
+            };
+            // gate of layer l: D1[l&1] -> h tile of parity l
+            auto gate = [&](int l) {
+                const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128 + lane_off;
+                unsigned char* th = t_h + (size_t)(l & 1) * TILE;
+                uint32_t ta[32], sa[32];
+                tmem_ldc(d1 + c32, ta);
+                tmem_ldc(d1 + 64 + c32, sa);
+                tmem_ld_wait();
+                if (tid == tr_tid) TRACE(0, 16);
+                uint32_t hp[CW / 2];
+#pragma unroll
+                for (int j = 0; j < CW; j += 2) {
+                    float a0 = __uint_as_float(ta[j]), a1 = __uint_as_float(ta[j + 1]);
+                    float g0 = __uint_as_float(sa[j]), g1 = __uint_as_float(sa[j + 1]);
+                    if (FUSED) {
+                        // the gate is MUFU-bound (2 transcendental per channel): evaluate both as packed fp16 pairs, one
+                        // MUFU.TANH per TWO values; h is rounded to fp16 for the next GEMM anyway
+                        a0 += cnd[j]; a1 += cnd[j + 1]; g0 += cnd[CW + j]; g1 += cnd[CW + j + 1];
+                        const __half2 th = wn::tanh_h2(__floats2half2_rn(a0, a1));
+                        const __half2 tg = wn::tanh_h2(__floats2half2_rn(0.5f * g0, 0.5f * g1));
+                        const __half2 hh = __hmul2(th, __hfma2(tg, __float2half2_rn(0.5f), __float2half2_rn(0.5f)));
+                        hp[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                    } else {
+                        const float h0 = wn::tanhf_fast(a0) * wn::sigmoidf_fast(g0);
+                        const float h1 = wn::tanhf_fast(a1) * wn::sigmoidf_fast(g1);
+                        hp[j >> 1] = pack_h2(h0, h1);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < CQ; q++) st_tile(th, q4 + q, make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]));
+                if (tid == tr_tid) TRACE(0, 12);
+            };
+            // residual of layer l: x += Dx + Bres (Dx in columns [0,64) of D1[l&1]); optionally -> x tile `xt`
+            auto residual = [&](int l, unsigned char* xt) {
+                const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128 + lane_off;
+                const float* br = s_bres + (size_t)l * 64 + c32;
+                uint32_t v[32];
+                tmem_ldc(d1 + c32, v);
+                tmem_ld_wait();
+                uint32_t o[CW / 2];
+#pragma unroll
+                for (int j = 0; j < CW; j += 2) {
+                    const float2 bb = *reinterpret_cast<const float2*>(br + j);
+                    float v0 = x[j] + (__uint_as_float(v[j]) + bb.x), v1 = x[j + 1] + (__uint_as_float(v[j + 1]) + bb.y);
+                    if (!valid) { v0 = 0.f; v1 = 0.f; }
+                    x[j] = v0; x[j + 1] = v1;
+                    o[j >> 1] = pack_h2(v0, v1);
+                }
+                if (xt) {
+#pragma unroll
+                    for (int q = 0; q < CQ; q++) st_tile(xt, q4 + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+                }
+                if (dump && valid) {                                    // last sample of a dumping launch only
+#pragma unroll
+                    for (int j = 0; j < CW; j++) p.xtOut[((size_t)l * B + b) * R + c32 + j] = x[j];
+                }
+            };
+            // dump only: skip sum through layer l (complete, and the next contribution not yet issued, at the call sites)
+            auto dump_skip = [&](int l) {
+                const int c_lo = sub * (S / NS);
+                for (int c0 = c_lo; c0 < c_lo + S / NS; c0 += 16) {
+                    uint32_t w[16];
+                    tmem_ld16(DSKIP + lane_off + c0, w);
+                    tmem_ld_wait();
+                    if (valid)
+                        for (int j = 0; j < 16; j++)
+                            p.skipOut[((size_t)l * B + b) * S + c0 + j] = __uint_as_float(w[j]) + gbias[im.b_bskp + (size_t)l * S + c0 + j];
+                }
+            };
+
+            if (FUSED) {
+                for (int l = 0; l < L; l++) {
+                    load_cond(l);                                       // in the shadow of the residual GEMM
+                    if (tid == tr_tid) TRACE(0, 5);
+                    if (l > 0) {
+                        // x_l = x_{l-1} + Wres_{l-1}.h_{l-1} + Bres_{l-1}: needed by the NEXT layer's background GEMM and the history
+                        mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
+                        tc_fence_after_sync();
+                        if (tid == tr_tid) TRACE(0, 4);
+                        if (wv) residual(l - 1, (l & 1) ? t_x1 : t_xc);
+                        tc_fence_before_sync();                         // x_l tile published, Dx consumed
+                        fence_proxy_async_smem();
+                        mbar_arrive(pre_done);
+                        if (tid == tr_tid) TRACE(0, 13);
+                    }
+                    mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
+                    tc_fence_after_sync();
+                    if (tid == tr_tid) TRACE(0, 2);
+                    if (wv) gate(l);
+                    if (dump && l > 0 && wv) dump_skip(l - 1);
+                    publish();                                          // h_l ready, D1[l&1] drained
+                    if (tid == tr_tid) TRACE(0, 3);
+                }
+                if (dump) {
+                    mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
+                    tc_fence_after_sync();
+                    if (wv) residual(L - 1, nullptr);
+                }
+            } else
+            for (int l = 0; l < L; l++) {
+                // ---------------- gate: h = tanh(a[0:R]) * sigmoid(a[R:2R]); D1 already holds the complete pre-activation
+                // a = (Lh[t][l] + Bh) + Wprev.x[t-d] + Wcur.x[t]   (reference.cpp:67-80)
+                mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
+                tc_fence_after_sync();
+                if (tid == tr_tid) TRACE(0, 2);
+                if (wv) gate(l);
+                publish();                                              // h ready, D1 drained
+                if (tid == tr_tid) TRACE(0, 3);
+                if (l + 1 < L) prestore(l + 1);                         // while the residual GEMM runs
+                // ---------------- residual: x += Dx + Bres   (reference.cpp:82-84)
+                mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
+                tc_fence_after_sync();
+                if (tid == tr_tid) TRACE(0, 4);
+                if (wv) {
+                    residual(l, (l + 1 < L) ? t_xc : nullptr);
+                    // skip sum through layer l-1 is complete here (its MMAs precede this layer's residual GEMM) and the
+                    // next contribution is only issued after the arrival below: no extra barrier needed
+                    if (dump && l > 0) dump_skip(l - 1);
+                }
                 if (l + 1 < L) {
                     publish();                                          // x_{l+1} ready
-                    if (tid == 0) TRACE(0, 5);
+                    if (tid == tr_tid) TRACE(0, 5);
                     if (wv) store_history(ring_tile(t, l + 1));
                 }
             }
@@ -644,17 +895,17 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             // ---------------- relu(skip) -> GEMM input of the first output layer   (reference.cpp:88-90)
             mbar_wait(skip_full, ph_skip); ph_skip ^= 1;
             tc_fence_after_sync();
-            if (tid == 0) TRACE(0, 6);
+            if (tid == tr_tid) TRACE(0, 6);
             if (wv) relu_to_tile(DSKIP, s_bsk, S, dump ? p.skipOut + ((size_t)(L - 1) * B + b) * S : nullptr);
             publish();                                                  // relu(skip) tile ready
-            if (tid == 0) TRACE(0, 7);
+            if (tid == tr_tid) TRACE(0, 7);
 
             // ---------------- Zs = relu(Wzs . skip + Bzs)   (reference.cpp:96-98)
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
             if (wv) relu_to_tile(DZS, s_bzs, A, dump ? p.Zs + (size_t)b * A : nullptr);
             publish();                                                  // relu(Zs) tile ready
-            if (tid == 0) TRACE(0, 9);
+            if (tid == tr_tid) TRACE(0, 9);
 
             // ---------------- Za, softmax, categorical sample   (reference.cpp:100-121)
             // The two threads of an utterance each take 128 logits: one TMEM pass parks them as fp16 in the thread's own row
@@ -662,7 +913,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             // halves meet through s_pair (local max, local sum) and s_y.
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
-            if (tid == 0) TRACE(0, 10);
+            if (tid == tr_tid) TRACE(0, 10);
             constexpr int PART = A / NS, NCH = PART / 16;               // logits per thread, 16-logit chunks per thread
             const int a_lo = sub * PART;
             float mx = 0.f;                                             // matrix.cpp:171 starts the max at 0
@@ -779,7 +1030,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 yp = yc;
                 yc = fb;
             }
-            if (tid == 0) TRACE(0, 11);
+            if (tid == tr_tid) TRACE(0, 11);
             // Dza is consumed: the x_0-ready arrival of the next sample (or kernel end) releases it
         }
         if (valid && sub == 0) { p.yPrev[b] = yp; p.yCur[b] = yc; }
@@ -851,14 +1102,17 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t 
     cudaError_t e = cudaErrorInvalidValue;
     const bool dup = TU == 64;                                  // tiles of at most 64 utterances: 4 threads per utterance
     const unsigned char* im8 = static_cast<const unsigned char*>(tc_image_);
-#define WN_TC_LAUNCH(SV, DV)                                                                                         \
+    static const bool fused = []() { const char* v = getenv("NVWN_TC_FUSED"); return !(v && v[0] == '0'); }();
+#define WN_TC_LAUNCH(SV, DV, FV)                                                                                     \
     do {                                                                                                             \
-        e = cudaFuncSetAttribute(wn_tc_kernel<SV, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        e = cudaFuncSetAttribute(wn_tc_kernel<SV, DV, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
         if (e != cudaSuccess) return e;                                                                              \
-        wn_tc_kernel<SV, DV><<<grid, NT, smem, stream>>>(p, im8, nstage);                                           \
+        wn_tc_kernel<SV, DV, FV><<<grid, NT, smem, stream>>>(p, im8, nstage);                                       \
     } while (0)
-    if (p.S == 256) { if (dup) WN_TC_LAUNCH(256, true); else WN_TC_LAUNCH(256, false); }
-    else { if (dup) WN_TC_LAUNCH(128, true); else WN_TC_LAUNCH(128, false); }
+#define WN_TC_LAUNCH2(SV, DV) do { if (fused) WN_TC_LAUNCH(SV, DV, true); else WN_TC_LAUNCH(SV, DV, false); } while (0)
+    if (p.S == 256) { if (dup) WN_TC_LAUNCH2(256, true); else WN_TC_LAUNCH2(256, false); }
+    else { if (dup) WN_TC_LAUNCH2(128, true); else WN_TC_LAUNCH2(128, false); }
+#undef WN_TC_LAUNCH2
 #undef WN_TC_LAUNCH
     if (info) { info->kernel = 17; info->grid = grid; info->block = NT; info->smem_bytes = (int)smem; info->batch_per_cta = dup ? 64 : 128; info->cluster = 1; }
     return cudaGetLastError();
