@@ -28,7 +28,7 @@ using namespace sm100;
 
 constexpr int R = 64, A = 256;
 constexpr int TILE = 16384;                 // [128 rows x 64 fp16] K-major SW128
-constexpr int NT = 320;                     // 8 epilogue warps + TMA producer warp + MMA issuer warp
+constexpr int NT = 384;                     // 8 epilogue warps + TMA producer warp + 2 MMA issuer warps + history-copy warp
 constexpr int NEPI = 256;
 
 struct TcImage {                            // byte offsets inside the packed image
@@ -57,7 +57,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int S, int L, int nstage)
 {
     // 4 activation tiles + weight ring + conditioning buffers (2 tiles) + biases (Bh, Bres, Bskip-sum, Bzs, Bza) + dilations + barriers
     return 1024 + 4 * (size_t)TILE + (size_t)nstage * TILE + 2 * TILE + ((size_t)L * 192 + S + 2 * A) * sizeof(float) + (size_t)L * 4 +
-           128 * 5 * sizeof(float) + (2 * nstage + 16) * 8 + 16;
+           128 * 5 * sizeof(float) + (2 * nstage + 20) * 8 + 16;
 }
 
 // Conditioning in the tensor-core layout: fp16 [N][L][Bpad rows][2 halves of 64 channels], tiled per 128 utterances;
@@ -223,7 +223,11 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     uint64_t* pre_done = epi_done + 5;          // accumulator of the coming layer initialised with Lh + bias
     uint64_t* cond_full = epi_done + 6;         // [NC]
     uint64_t* cond_empty = epi_done + 8;        // [NC]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 12);
+    uint64_t* cx_done = epi_done + 10;          // fused schedule, see the issuer roles
+    uint64_t* b_done = epi_done + 11;           // [2] at +11, +14: alternating by layer parity, so that the signalling role can
+    uint64_t* hx_full = epi_done + 12;          //     never complete a barrier twice before its waiter has looked once
+    uint64_t* hx_done = epi_done + 13;          // [2] at +13, +15
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 16);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, ntiles = gridDim.x;
@@ -237,7 +241,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     if (tid == 0) {
         for (int s = 0; s < nstage; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         mbar_init(epi_done, NEPI);
-        mbar_init(d1_full, 1); mbar_init(dx_full, 1); mbar_init(skip_full, 1); mbar_init(out_full, 1);
+        mbar_init(d1_full, 1); mbar_init(dx_full, 1); mbar_init(skip_full, FUSED ? 2 : 1); mbar_init(out_full, FUSED ? 2 : 1);
+        mbar_init(cx_done, 1); mbar_init(b_done, 1); mbar_init(b_done + 3, 1); mbar_init(hx_full, NEPI); mbar_init(hx_done, 1); mbar_init(hx_done + 2, 1);
         mbar_init(pre_done, NEPI);
         for (int i = 0; i < NC; i++) { mbar_init(&cond_full[i], 1); mbar_init(&cond_empty[i], NEPI); }
         fence_mbar_init();
@@ -383,8 +388,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 for (int c = 0; c < (S / 64) * 2 + (A / 64) * 2; c++) put(ow + (size_t)c * TILE, TILE);
             }
         }
-    } else if (warp == 9) {
-        // =============================================================== MMA issuer (whole warp converged, one lane issues)
+    } else if (warp >= 9) {
+        // =============================================================== MMA issuer(s) (whole warp converged, one lane issues)
         {
             const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
             int stage = 0;
@@ -472,91 +477,183 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     }
             };
             if (FUSED) {
-                // Per gate h_{l-1}: res(l-1) [-> x_l, off the critical path] | Wf(l) -> commit d1_full (the only GEMM the next
-                // gate waits for) | skip(l-1) | then, once the epilogue has initialised D1 of layer l+1: prev(l+1) and
-                // Wcur_{l+1}.x_l in the background.
+                // Three single-lane roles share the issue work, which -- not the tensor pipe -- bounds a one-CTA layer
+                // (every group of 4 MMAs + commits costs its issuing thread ~350 cycles, every mbarrier wait ~100):
+                //   A (warp 9)  critical path: per gate h_{l-1}: res(l-1) -> dx_full | Wf(l) -> d1_full | Wcur_{l+1}.x_l
+                //   B (warp 10) background:    skip(l-1) | Wprev_{l+1}.x_{l+1}[t-d]      (+ the nh = 1 half of Zs / Za)
+                //   C (warp 11) history ring:  published x_l tile -> global, one bulk copy (async proxy on both ends)
+                // All walk the same chunk sequence of the weight ring and wait only for their own chunks.
+                //   cx_done  A -> B: Wcur_{l+1}.x_l (which OVERWRITES D1) has completed, Wprev may accumulate
+                //   b_done   B -> A: skip(l-1) [h tile of that parity reusable] and prev(l+1) completed; A waits for it before
+                //                    committing d1_full(l+1), which also bounds how far B can fall behind
+                //   hx_full  epilogue -> C, hx_done C -> A: the copy of x_{l-1} has fully completed before A commits dx_full(l-1)
+                //                    (whose consumer overwrites an x tile) and before the commits that let the producer run on
                 const uint64_t d_x[2] = {d_xc, d_big + 3 * TILE_D};
-                // History ring: the published x_l tile goes shared -> global as ONE bulk copy issued here (async proxy on both
-                // ends: no generic-proxy stores + proxy fences in 256 epilogue threads).  Lane 0 owns the bulk group; it
-                // waits for completion one layer later, before the commits that (through the weight ring) let the producer
-                // run ahead to the loads of the next sample, and before the tile is overwritten.
-                const uint32_t hist_bytes = (uint32_t)(DUP ? TILE / 2 : TILE);
-                auto hist_store = [&](int t, int l) {
-                    if (lane == 0) tma_store_1d(ring_tile(t, l), (l & 1) ? t_x1 : t_xc, hist_bytes);
-                    __syncwarp();
+                const int role = warp - 9;
+                uint32_t ph_cx = 0, ph_b = 0, ph_hx = 0;           // ph_b / ph_hx: bit k = phase of barrier k of the pair
+                auto wait2 = [&](uint64_t* pair, int stride, uint32_t& ph, int k) {
+                    mbar_wait(pair + (k & 1) * stride, (ph >> (k & 1)) & 1u);
+                    ph ^= 1u << (k & 1);
                 };
-                auto hist_wait = [&]() { if (lane == 0) tma_store_wait_all(); __syncwarp(); };
-                for (int t = t_begin; t < t_end; t++) {
-                    const bool dstep = p.dump && (t == t_end - 1);
-                    uint64_t dw;
-                    wait_epi();                                         // x_0 tile ready (and Dza of the previous sample consumed)
-                    hist_store(t, 0);
-                    if (lane == 0) TRACE(1, 20);
-                    open_f(0, t >= 1, false);
-                    dw = wait_stage();
-                    tc_fence_after_sync();
-                    mma4(d_x[0], dw, D1B, idesc128, t >= 1, d1_full, &w_empty[stage]);      // D1[0] (+)= Wcur_0 . x_0
-                    advance();
-                    if (L > 1) {
-                        open_f(1, t >= s_dil[1], false);
-                        dw = wait_stage();
-                        tc_fence_after_sync();
-                        mma4(d_x[0], dw, D1B + 128, idesc128, t >= s_dil[1], nullptr, &w_empty[stage]);   // D1[1] (+)= Wcur_1 . x_0
-                        advance();
-                    }
-                    for (int l = 1; l < L; l++) {
-                        const uint64_t dh = d_h + (uint64_t)((l - 1) & 1) * TILE_D;
-                        dw = wait_stage();                              // Wres_{l-1} already landed when h arrives
-                        wait_epi();                                     // h_{l-1} ready, D1[(l-1)&1] drained
-                        if (lane == 0) TRACE(1, 22);
-                        hist_wait();
-                        if (lane == 0) TRACE(1, 28);
-                        if (elect_one()) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) umma_f16(D1B + (uint32_t)((l - 1) & 1) * 128, dh + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc64, k ? 1u : 0u);
+                auto skipc = [&](int n) { for (int i = 0; i < n; i++) advance(); };
+                constexpr int SKC = S / 128;
+                if (role == 2) {
+                    const uint32_t hist_bytes = (uint32_t)(DUP ? TILE / 2 : TILE);
+                    for (int t = t_begin; t < t_end; t++)
+                        for (int l = 0; l < L; l++) {
+                            mbar_wait(hx_full, ph_hx); ph_hx ^= 1;
+                            if (lane == 0) {
+                                tma_store_1d(ring_tile(t, l), (l & 1) ? t_x1 : t_xc, hist_bytes);
+                                tma_store_wait_all();
+                                mbar_arrive(hx_done + (l & 1) * 2);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
-                        if (lane == 0) TRACE(1, 26);
-                        if (elect_one()) { umma_commit(dx_full); umma_commit(&w_empty[stage]); }
-                        __syncwarp();
-                        advance();
-                        if (lane == 0) TRACE(1, 25);
-                        if (dstep) skip_layer(l - 1, nullptr);
+                } else if (role == 0) {
+                    for (int t = t_begin; t < t_end; t++) {
+                        const bool dstep = p.dump && (t == t_end - 1);
+                        uint64_t dw;
+                        wait_epi();                                     // x_0 tile ready (and Dza of the previous sample consumed)
+                        if (lane == 0) TRACE(1, 20);
+                        open_f(0, t >= 1, false);                       // Wprev_0 . x_0[t-1] stays with A (start of the chain)
                         dw = wait_stage();
                         tc_fence_after_sync();
-                        if (lane == 0) TRACE(1, 29);
-                        mma4(dh, dw, D1B + (uint32_t)(l & 1) * 128, idesc128, true, d1_full, &w_empty[stage]);         // D1[l] += Wf_l . h
+                        mma4(d_x[0], dw, D1B, idesc128, t >= 1, d1_full, &w_empty[stage]);          // D1[0] (+)= Wcur_0 . x_0
                         advance();
-                        if (lane == 0) TRACE(1, 21);
-                        if (!dstep) skip_layer(l - 1, nullptr);
-                        if (lane == 0) TRACE(1, 23);
-                        if (l + 1 < L) {
-                            open_f(l + 1, t >= s_dil[l + 1], true);     // waits: x_l tile published, Dx of layer l-1 consumed
-                            if (lane == 0) TRACE(1, 32);
+                        if (L > 1) {
+                            const bool hp = t >= s_dil[1];
+                            if (hp) skipc(2);                           // B: Wprev_1
                             dw = wait_stage();
                             tc_fence_after_sync();
-                            if (lane == 0) TRACE(1, 33);
-                            mma4(d_x[l & 1], dw, D1B + (uint32_t)((l + 1) & 1) * 128, idesc128, t >= s_dil[l + 1], nullptr, &w_empty[stage]);   // (+)= Wcur_{l+1} . x_l
+                            mma4(d_x[0], dw, D1B + 128, idesc128, false, hp ? cx_done : nullptr, &w_empty[stage]);   // D1[1] = Wcur_1 . x_0
                             advance();
-                        } else {
-                            mbar_wait(pre_done, ph_pre); ph_pre ^= 1;   // x_{L-1} tile published (history only)
                         }
-                        if (lane == 0) TRACE(1, 34);
-                        hist_store(t, l);
-                        if (lane == 0) TRACE(1, 24);
+                        for (int l = 1; l < L; l++) {
+                            const uint64_t dh = d_h + (uint64_t)((l - 1) & 1) * TILE_D;
+                            const bool hpn = (l + 1 < L) && t >= s_dil[l + 1];
+                            dw = wait_stage();                          // Wres_{l-1} already landed when h arrives
+                            wait_epi();                                 // h_{l-1} ready, D1[(l-1)&1] drained
+                            if (lane == 0) TRACE(1, 22);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) umma_f16(D1B + (uint32_t)((l - 1) & 1) * 128, dh + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc64, k ? 1u : 0u);
+                            }
+                            __syncwarp();
+                            if (elect_one()) { umma_commit(dx_full); umma_commit(&w_empty[stage]); }
+                            __syncwarp();
+                            advance();
+                            if (lane == 0) TRACE(1, 25);
+                            if (dstep) skip_layer(l - 1, nullptr);      // dumping sample: the skip sum through l-1 must be complete at gate l
+                            dw = wait_stage();
+                            tc_fence_after_sync();
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) umma_f16(D1B + (uint32_t)(l & 1) * 128, dh + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc128, 1u);   // D1[l] += Wf_l . h
+                            }
+                            __syncwarp();
+                            wait2(b_done, 3, ph_b, l - 1);              // B's share of D1[l] is in; h tile of parity l is free
+                            if (elect_one()) { umma_commit(d1_full); umma_commit(&w_empty[stage]); }
+                            __syncwarp();
+                            advance();
+                            if (lane == 0) TRACE(1, 21);
+                            if (!dstep) skipc(SKC);                     // B: skip(l-1)
+                            // history copy of x_{l-1} complete: before dx_full(l), whose consumer overwrites that x tile, and
+                            // before any further commit lets the producer run on
+                            wait2(hx_done, 2, ph_hx, l - 1);
+                            mbar_wait(pre_done, ph_pre); ph_pre ^= 1;   // x_l tile published, Dx of layer l-1 consumed
+                            tc_fence_after_sync();
+                            if (l + 1 < L) {
+                                if (hpn) skipc(2);                      // B: Wprev_{l+1}
+                                dw = wait_stage();
+                                tc_fence_after_sync();
+                                mma4(d_x[l & 1], dw, D1B + (uint32_t)((l + 1) & 1) * 128, idesc128, false, hpn ? cx_done : nullptr, &w_empty[stage]);   // = Wcur_{l+1} . x_l
+                                advance();
+                            }
+                            if (lane == 0) TRACE(1, 24);
+                        }
+                        wait_epi();                                     // h_{L-1}
+                        wait2(hx_done, 2, ph_hx, L - 1);                // x_{L-1} copied: the activation tiles may be reused
+                        if (L > 1) wait2(b_done, 3, ph_b, L - 1);
+                        if (dstep) {
+                            dw = wait_stage();
+                            tc_fence_after_sync();
+                            mma4(d_h + (uint64_t)((L - 1) & 1) * TILE_D, dw, D1B + (uint32_t)((L - 1) & 1) * 128, idesc64, false, dx_full, &w_empty[stage]);
+                            advance();
+                            skip_layer(L - 1, skip_full);
+                        } else {
+                            skipc(SKC);
+                        }
+                        if (lane == 0) mbar_arrive(skip_full);          // second arrival: this role's conditions for the output phase
+                        __syncwarp();
+                        // output GEMMs: A takes the nh = 0 half of the columns, B the other
+                        for (int g = 0; g < 2; g++) {
+                            wait_epi();                                 // relu(skip) / relu(Zs) tile ready
+                            const int KT = g ? A / 64 : S / 64;
+                            for (int kt = 0; kt < KT; kt++) {
+                                dw = wait_stage();
+                                tc_fence_after_sync();
+                                mma4(d_big + (uint64_t)kt * TILE_D, dw, (g ? DZA : DZS), idesc128, kt > 0, &w_empty[stage], kt == KT - 1 ? out_full : nullptr);
+                                advance();
+                                skipc(1);
+                            }
+                        }
                     }
-                    wait_epi();                                         // h_{L-1}
-                    hist_wait();
-                    if (dstep) {
-                        dw = wait_stage();
-                        tc_fence_after_sync();
-                        mma4(d_h + (uint64_t)((L - 1) & 1) * TILE_D, dw, D1B + (uint32_t)((L - 1) & 1) * 128, idesc64, false, dx_full, &w_empty[stage]);
-                        advance();
+                } else {
+                    for (int t = t_begin; t < t_end; t++) {
+                        const bool dstep = p.dump && (t == t_end - 1);
+                        auto prev_b = [&](int l) {                      // D1[l&1] += Wprev_l . x_l[t-d], after A's overwrite has completed
+                            mbar_wait(cx_done, ph_cx); ph_cx ^= 1;
+                            const uint64_t da = wait_stage();
+                            const int sa = stage;
+                            advance();
+                            const uint64_t db = wait_stage();
+                            tc_fence_after_sync();
+                            mma4(da, db, D1B + (uint32_t)(l & 1) * 128, idesc128, true, &w_empty[sa], &w_empty[stage]);
+                            advance();
+                        };
+                        // b_done: tcgen05.commit when this role issued MMAs since its last signal, a plain arrival otherwise
+                        auto commit_b = [&](bool had_mma, int j) {          // j = 0 at the start of the sample, l in the loop
+                            uint64_t* bar = b_done + (j & 1) * 3;
+                            if (elect_one()) { if (had_mma) umma_commit(bar); else mbar_arrive(bar); }
+                            __syncwarp();
+                        };
+                        wait_epi();                                     // x_0
+                        if (t >= 1) skipc(2);                           // A: Wprev_0
+                        skipc(1);                                       // A: Wcur_0
+                        if (L > 1) {
+                            if (t >= s_dil[1]) prev_b(1);
+                            skipc(1);                                   // A: Wcur_1
+                            commit_b(t >= s_dil[1], 0);
+                        }
+                        for (int l = 1; l < L; l++) {
+                            skipc(1);                                   // A: Wres_{l-1}
+                            wait_epi();                                 // h_{l-1}
+                            if (dstep) skipc(SKC + 1);                  // A: skip(l-1), Wf_l
+                            else { skipc(1); skip_layer(l - 1, nullptr); }
+                            const bool hpn = (l + 1 < L) && t >= s_dil[l + 1];
+                            if (l + 1 < L) {
+                                if (hpn) prev_b(l + 1);
+                                skipc(1);                               // A: Wcur_{l+1}
+                            }
+                            commit_b(!dstep || hpn, l);
+                        }
+                        wait_epi();                                     // h_{L-1}
+                        if (dstep) skipc(1 + SKC);
+                        else skip_layer(L - 1, skip_full);
+                        for (int g = 0; g < 2; g++) {
+                            wait_epi();
+                            const int KT = g ? A / 64 : S / 64;
+                            for (int kt = 0; kt < KT; kt++) {
+                                skipc(1);
+                                const uint64_t dw = wait_stage();
+                                tc_fence_after_sync();
+                                mma4(d_big + (uint64_t)kt * TILE_D, dw, (g ? DZA : DZS) + 128, idesc128, kt > 0, &w_empty[stage], kt == KT - 1 ? out_full : nullptr);
+                                advance();
+                            }
+                        }
                     }
-                    skip_layer(L - 1, skip_full);
-                    out_gemms();
                 }
-            } else
+            } else if (warp == 9)
             for (int t = t_begin; t < t_end; t++) {
                 int d = 1;                                              // dilation of layer l (nv_wavenet.cuh:99-111)
                 for (int l = 0; l < L; l++) {
@@ -735,6 +832,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 }
             }
             publish();                                                  // x_0 ready
+            if (FUSED) mbar_arrive(hx_full);
             if (tid == tr_tid) TRACE(0, 1);
             if (!FUSED && wv) store_history(ring_tile(t, 0));
 
@@ -849,6 +947,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         tc_fence_before_sync();                         // x_l tile published, Dx consumed
                         fence_proxy_async_smem();
                         mbar_arrive(pre_done);
+                        mbar_arrive(hx_full);
                         if (tid == tr_tid) TRACE(0, 13);
                     }
                     mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
