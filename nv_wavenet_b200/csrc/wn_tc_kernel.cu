@@ -446,12 +446,22 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             // skip(l): Dskip (+)= Wskip_l . h_l, h_l in the H buffer of parity l
             auto skip_layer = [&](int l, uint64_t* done_bar) {
                 const uint64_t dh = d_h + (uint64_t)(l & 1) * TILE_D;
-                for (int c = 0; c < S / 128; c++) {
-                    const uint64_t dw = wait_stage();
-                    tc_fence_after_sync();
-                    mma4(dh, dw, DSKIP + c * 128, idesc128, l > 0, &w_empty[stage], (c == S / 128 - 1) ? done_bar : nullptr);
-                    advance();
+                // all S/128 chunks as ONE issue block: a single election, the commits at the end
+                uint64_t dws[S / 128];
+                int sts[S / 128];
+#pragma unroll
+                for (int c = 0; c < S / 128; c++) { dws[c] = wait_stage(); sts[c] = stage; advance(); }
+                tc_fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (int c = 0; c < S / 128; c++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma_f16(DSKIP + c * 128, dh + (uint64_t)(2 * k), dws[c] + (uint64_t)(2 * k), idesc128, (l > 0 || k) ? 1u : 0u);
+#pragma unroll
+                    for (int c = 0; c < S / 128; c++) umma_commit(&w_empty[sts[c]]);
+                    if (done_bar) umma_commit(done_bar);
                 }
+                __syncwarp();
             };
             // Issue order per layer: cur(l) | skip(l-1) in the shadow of the gate epilogue | res(l) | prev(l+1) in the shadow
             // of the residual epilogue.  Nothing but cur / res sits between an epilogue arrival and the accumulator it
@@ -532,6 +542,10 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                             const uint64_t dh = d_h + (uint64_t)((l - 1) & 1) * TILE_D;
                             const bool hpn = (l + 1 < L) && t >= s_dil[l + 1];
                             dw = wait_stage();                          // Wres_{l-1} already landed when h arrives
+                            if (!dstep) {                               // ... and so has Wf_l, the next chunk of the sequence
+                                const int s1 = (stage + 1 == nstage) ? 0 : stage + 1;
+                                mbar_wait(&w_full[s1], s1 ? ph_full : (ph_full ^ 1u));
+                            }
                             wait_epi();                                 // h_{l-1} ready, D1[(l-1)&1] drained
                             if (lane == 0) TRACE(1, 22);
                             if (elect_one()) {
@@ -792,11 +806,17 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 tmem_ld_wait();
                 uint32_t o[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float v0 = fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + bias[c0 + j + 1], 0.f);
-                    if (!valid) { v0 = 0.f; v1 = 0.f; }
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + j);
+                    float v0 = fmaxf(__uint_as_float(v[j]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
+                    float v2 = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
+                    if (!valid) { v0 = 0.f; v1 = 0.f; v2 = 0.f; v3 = 0.f; }
                     o[j >> 1] = pack_h2(v0, v1);
-                    if (dump_dst && valid) { dump_dst[c0 + j] = v0; dump_dst[c0 + j + 1] = v1; }
+                    o[(j >> 1) + 1] = pack_h2(v2, v3);
+                }
+                if (dump_dst && valid) {                                // last sample of a dumping launch only
+#pragma unroll
+                    for (int j = 0; j < 32; j++) dump_dst[c0 + j] = fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f);
                 }
                 unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;
                 const int q = (c0 & 63) >> 3;
@@ -1201,7 +1221,11 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t 
     cudaError_t e = cudaErrorInvalidValue;
     const bool dup = TU == 64;                                  // tiles of at most 64 utterances: 4 threads per utterance
     const unsigned char* im8 = static_cast<const unsigned char*>(tc_image_);
-    static const bool fused = []() { const char* v = getenv("NVWN_TC_FUSED"); return !(v && v[0] == '0'); }();
+    // Fused schedule (one MMA<->epilogue round trip per layer, +1 weight chunk per layer) while the launch is latency-bound;
+    // with (nearly) every SM streaming the weights from L2 the extra chunk costs more than the round trip saves
+    // (measured, 64-utterance tiles: 2048 utt. 50.9M vs 44.5M samples/s fused; 9472 utt. 175.6M fused vs 196.4M unfused).
+    static const int fused_env = []() { const char* v = getenv("NVWN_TC_FUSED"); return v ? (v[0] == '0' ? 0 : 1) : -1; }();
+    const bool fused = fused_env >= 0 ? fused_env == 1 : !(TU == 64 && grid > 96);
 #define WN_TC_LAUNCH(SV, DV, FV)                                                                                     \
     do {                                                                                                             \
         e = cudaFuncSetAttribute(wn_tc_kernel<SV, DV, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
