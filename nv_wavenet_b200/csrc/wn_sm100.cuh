@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 21)) mbar_timeout(smem_u32(bar), parity);
+        if (++spins > (1u << 24)) mbar_timeout(smem_u32(bar), parity);
     }
 }
 
