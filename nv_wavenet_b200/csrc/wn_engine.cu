@@ -20,8 +20,8 @@ bool wn_tc_supported(int R, int S, int A, int L, int B);
 size_t wn_tc_image_bytes(int R, int S, int A, int L);
 cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream);
 size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B);
-size_t wn_tc_cond_bytes(int L, int B, int N);
-cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
+size_t wn_tc_cond_bytes(int S, int L, int B, int N);
+cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream);
 
 namespace {
 
@@ -205,7 +205,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     } while (0)
     ALLOC(e->blob, e->blob_bytes);
     e->tc_mode = decide_tc(dtype, impl, R, S, A, num_layers, batch_size);
-    ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(num_layers, batch_size, num_samples) : Nz * L * Bz * 2 * R * td);
+    ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(S, num_layers, batch_size, num_samples) : Nz * L * Bz * 2 * R * td);
     ALLOC(e->sel, Nz * Bz * sizeof(float));
     ALLOC(e->forced, Nz * Bz * sizeof(int));
     ALLOC(e->yPrev, Bz * sizeof(int));
@@ -316,7 +316,7 @@ int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int
     // an MMA operand tile (wn_tc_kernel.cu).  Host sources bounce through the staging buffer in whole samples.
     cudaStream_t st = (cudaStream_t)stream;
     if (is_device_ptr(Lh)) {
-        CK(wn_tc_cond_convert(e->Lh, Lh, first_sample, num_samples, e->L, e->B, st));
+        CK(wn_tc_cond_convert(e->Lh, Lh, first_sample, num_samples, e->S, e->L, e->B, st));
         return 0;
     }
     const int chunk = (int)(e->stage_elems / per);
@@ -324,7 +324,7 @@ int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int
     for (int done = 0; done < num_samples; done += chunk) {
         const int m = (num_samples - done < chunk) ? num_samples - done : chunk;
         CK(cudaMemcpyAsync(e->stage_dev, Lh + (size_t)done * per, (size_t)m * per * sizeof(float), cudaMemcpyHostToDevice, st));
-        CK(wn_tc_cond_convert(e->Lh, e->stage_dev, first_sample + done, m, e->L, e->B, st));
+        CK(wn_tc_cond_convert(e->Lh, e->stage_dev, first_sample + done, m, e->S, e->L, e->B, st));
     }
     return 0;
 }

@@ -185,9 +185,12 @@ __device__ __forceinline__ uint32_t chunk_off(int row, int q) { return (uint32_t
 // + Wf_l.h_{l-1} [the only GEMM on the critical path], Wf_l = Wcur_l.Wres_{l-1} folded at pack time.  The residual GEMM
 // Wres_{l-1}.h_{l-1} still produces x_l (history ring, next layer's background GEMM, dump) but nothing waits on it
 // before the next gate.
-template <int S, bool DUP, bool FUSED>
+template <int S, int CP, bool FUSED>
 __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const unsigned char* __restrict__ img, const int nstage)
 {
+    // CP = row copies per utterance (1, 2, 4): tiles of 128 / CP utterances, 2 CP threads per utterance.  CP = 4 spreads a
+    // small batch over twice the SMs of CP = 2 and halves the per-thread gate / residual / softmax work once more.
+    constexpr bool DUP = CP > 1;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment by OFFSET (not by pointer round-trip through an integer): the compiler keeps knowing these
     // are shared-memory addresses and emits LDS/STS instead of generic LD/ST
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     const uint32_t D1B = tmem_base, DSKIP = tmem_base + 256, DZS = tmem_base + 256, DZA = tmem_base;
 
     // conditioning tile geometry (see tc_cond_kernel)
-    constexpr int TU = DUP ? 64 : 128;              // utterances per tile
+    constexpr int TU = 128 / CP;                    // utterances per tile
     const int c_rows = cond_rows(B, tile, TU);
     const uint32_t c_bytes = (uint32_t)c_rows * 128u;
     const size_t c_bpad = cond_bpad(B, TU);
@@ -302,9 +305,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 if (!DUP) { put(src, bytes); return; }
                 mbar_wait(&w_empty[stage], ph);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&w_full[stage], 2 * bytes);
-                    tma_load_1d(ring + (size_t)stage * TILE, src, bytes, &w_full[stage]);
-                    tma_load_1d(ring + (size_t)stage * TILE + TILE / 2, src, bytes, &w_full[stage]);
+                    mbar_arrive_expect_tx(&w_full[stage], CP * bytes);
+#pragma unroll
+                    for (int k = 0; k < CP; k++) tma_load_1d(ring + (size_t)stage * TILE + (size_t)k * (TILE / CP), src, bytes, &w_full[stage]);
                 }
                 __syncwarp();
                 if (++stage == nstage) { stage = 0; ph ^= 1; }
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             //   prev(0) | cur(0) res(0) prev(1) | cur(1) skip(0) res(1) prev(2) | ... | cur(L-1) skip(L-2) res(L-1) | skip(L-1) | Wzs | Wza
             // where prev(l) = the x[t-d_l] history tile + Wprev_l, present only if t >= d_l.
             auto put_prev = [&](int t, int l, int d) {
-                if (t >= d) { put_act(ring_tile(t - d, l), DUP ? TILE / 2 : TILE); put(img + (size_t)l * im.layer_bytes, TILE); }
+                if (t >= d) { put_act(ring_tile(t - d, l), TILE / CP); put(img + (size_t)l * im.layer_bytes, TILE); }
             };
             auto put_skip = [&](int l) {
                 for (int c = 0; c < S / 128; c++) put(img + (size_t)l * im.layer_bytes + 2 * TILE + TILE / 2 + (size_t)c * TILE, TILE);
@@ -494,13 +497,13 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 //   C (warp 11) history ring:  published x_l tile -> global, one bulk copy (async proxy on both ends)
                 // All walk the same chunk sequence of the weight ring and wait only for their own chunks.
                 //   cx_done  A -> B: Wcur_{l+1}.x_l (which OVERWRITES D1) has completed, Wprev may accumulate
-                //   b_done   B -> A: skip(l-1) [h tile of that parity reusable] and prev(l+1) completed; A waits for it before
-                //                    committing d1_full(l+1), which also bounds how far B can fall behind
+                //   b_done   B -> gate threads: skip(l-1) [h tile of that parity reusable] and prev(l+1) completed; awaited next to
+                //                    d1_full(l+1), which also bounds how far B can fall behind
                 //   hx_full  epilogue -> C, hx_done C -> A: the copy of x_{l-1} has fully completed before A commits dx_full(l-1)
                 //                    (whose consumer overwrites an x tile) and before the commits that let the producer run on
                 const uint64_t d_x[2] = {d_xc, d_big + 3 * TILE_D};
                 const int role = warp - 9;
-                uint32_t ph_cx = 0, ph_b = 0, ph_hx = 0;           // ph_b / ph_hx: bit k = phase of barrier k of the pair
+                uint32_t ph_cx = 0, ph_hx = 0;                     // ph_hx: bit k = phase of barrier k of the pair
                 auto wait2 = [&](uint64_t* pair, int stride, uint32_t& ph, int k) {
                     mbar_wait(pair + (k & 1) * stride, (ph >> (k & 1)) & 1u);
                     ph ^= 1u << (k & 1);
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 auto skipc = [&](int n) { for (int i = 0; i < n; i++) advance(); };
                 constexpr int SKC = S / 128;
                 if (role == 2) {
-                    const uint32_t hist_bytes = (uint32_t)(DUP ? TILE / 2 : TILE);
+                    const uint32_t hist_bytes = (uint32_t)(TILE / CP);
                     for (int t = t_begin; t < t_end; t++)
                         for (int l = 0; l < L; l++) {
                             mbar_wait(hx_full, ph_hx); ph_hx ^= 1;
@@ -565,7 +568,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                                 for (int k = 0; k < 4; k++) umma_f16(D1B + (uint32_t)(l & 1) * 128, dh + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc128, 1u);   // D1[l] += Wf_l . h
                             }
                             __syncwarp();
-                            wait2(b_done, 3, ph_b, l - 1);              // B's share of D1[l] is in; h tile of parity l is free
+                            // (a tcgen05.commit must follow its MMAs at once -- issued with nothing outstanding it never
+                            // arrives -- so B's share of D1[l] / the free h tile are awaited by the gate threads, not here)
                             if (elect_one()) { umma_commit(d1_full); umma_commit(&w_empty[stage]); }
                             __syncwarp();
                             advance();
@@ -587,7 +591,6 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         }
                         wait_epi();                                     // h_{L-1}
                         wait2(hx_done, 2, ph_hx, L - 1);                // x_{L-1} copied: the activation tiles may be reused
-                        if (L > 1) wait2(b_done, 3, ph_b, L - 1);
                         if (dstep) {
                             dw = wait_stage();
                             tc_fence_after_sync();
@@ -702,35 +705,39 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
         // Warp w works on TMEM lane quadrant w % 4 (hardware rule) and on channel half w / 4: thread (quad, lane, ch)
         // owns row 32*quad + lane and channels [32 ch, 32 ch + 32) of the 64-wide residual / gate, i.e. 16-byte chunks
         // 4 ch .. 4 ch + 3 of its row in every 128-byte tile row.  Two warps per scheduler hide each other's latencies.
-        constexpr int NS = DUP ? 4 : 2;                 // threads per utterance
+        constexpr int NS = 2 * CP;                      // threads per utterance
         constexpr int CW = 64 / NS;                     // residual / gate channels per thread
         constexpr int CQ = CW / 8;                      // 16-byte chunks per thread in a 128-byte tile row
         const int quad = warp & 3, ch = warp >> 2;
         const int row = quad * 32 + lane;               // TMEM lane / tile row this thread reads
-        const int u = DUP ? (row & 63) : row;           // utterance of the tile
-        const int sub = DUP ? (ch * 2 + (row >> 6)) : ch;   // which CW-wide slice of the channels is mine
+        const int u = row & (TU - 1);                   // utterance of the tile
+        const int sub = ch * CP + row / TU;             // which CW-wide slice of the channels is mine
         const int b = tile * TU + u;
         const bool valid = b < B;
-        const bool wv = tile * TU + (DUP ? (quad & 1) : quad) * 32 < B;   // warp has a live utterance: dead warps only keep
+        const bool wv = tile * TU + ((quad * 32) & (TU - 1)) < B;   // warp has a live utterance: dead warps only keep
                                                         // the barrier protocol going (their rows are never read back)
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const int c32 = CW * sub, q4 = CQ * sub;        // first channel / first chunk of this thread
         // rows of the activation tiles this thread writes: its own row, and with DUP the twin row of the utterance
-        const int row2 = DUP ? (row ^ 64) : row;
         auto st_tile = [&](unsigned char* tile_base, int q, uint4 v) {
-            *reinterpret_cast<uint4*>(tile_base + chunk_off(row, q)) = v;
-            if (DUP) *reinterpret_cast<uint4*>(tile_base + chunk_off(row2, q)) = v;
+#pragma unroll
+            for (int k = 0; k < CP; k++) *reinterpret_cast<uint4*>(tile_base + chunk_off(u + k * TU, q)) = v;   // same (row & 7): same swizzle
         };
         auto tmem_ldc = [&](uint32_t addr, uint32_t (&r)[32]) {       // CW columns into r[0..CW)
-            if (CW == 32) { tmem_ld32(addr, r); }
-            else {
+            if constexpr (CW == 32) { tmem_ld32(addr, r); }
+            else if constexpr (CW == 16) {
                 uint32_t t16[16];
                 tmem_ld16(addr, t16);
 #pragma unroll
                 for (int i = 0; i < 16; i++) r[i] = t16[i];
+            } else {
+                uint32_t t8[8];
+                tmem_ld8(addr, t8);
+#pragma unroll
+                for (int i = 0; i < 8; i++) r[i] = t8[i];
             }
         };
-        uint32_t ph_d1 = 0, ph_dx = 0, ph_skip = 0, ph_out = 0;
+        uint32_t ph_d1 = 0, ph_dx = 0, ph_skip = 0, ph_out = 0, ph_bd = 0;
         const __half* embPrev = static_cast<const __half*>(p.embPrev);
         const __half* embCur = static_cast<const __half*>(p.embCur);
         const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
@@ -786,7 +793,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         }
                     }
                     if constexpr (CW == 32) tmem_st32(d1n + 64 * half + c32, v);
-                    else tmem_st16(d1n + 64 * half + c32, v);
+                    else if constexpr (CW == 16) tmem_st16(d1n + 64 * half + c32, v);
+                    else tmem_st8(d1n + 64 * half + c32, v);
                 }
                 tmem_st_wait();
             }
@@ -969,6 +977,8 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                         mbar_arrive(pre_done);
                         mbar_arrive(hx_full);
                         if (tid == tr_tid) TRACE(0, 13);
+                        // B's share of this layer's accumulator (Wprev . x[t-d]) is complete and skip(l-2) has released the h tile
+                        mbar_wait(b_done + ((l - 1) & 1) * 3, (ph_bd >> ((l - 1) & 1)) & 1u); ph_bd ^= 1u << ((l - 1) & 1);
                     }
                     mbar_wait(d1_full, ph_d1); ph_d1 ^= 1;
                     tc_fence_after_sync();
@@ -978,6 +988,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     publish();                                          // h_l ready, D1[l&1] drained
                     if (tid == tr_tid) TRACE(0, 3);
                 }
+                if (L > 1) { mbar_wait(b_done + ((L - 1) & 1) * 3, (ph_bd >> ((L - 1) & 1)) & 1u); ph_bd ^= 1u << ((L - 1) & 1); }
                 if (dump) {
                     mbar_wait(dx_full, ph_dx); ph_dx ^= 1;
                     tc_fence_after_sync();
@@ -1178,27 +1189,31 @@ bool wn_tc_supported(int R_, int S, int A_, int L, int)
 size_t wn_tc_image_bytes(int, int S, int, int L) { return tc_image(S, L).total; }
 
 // 64-utterance tiles (the lower-latency four-threads-per-utterance variant) as long as one wave of CTAs covers the batch
-int wn_tc_tile_utt(int B)
+// Utterances per CTA tile: 32 (eight threads per utterance) while that keeps the launch small enough to stay latency-bound,
+// 64 as long as one wave of CTAs covers the batch, else full 128-row tiles.  NVWN_TC_TILE / NVWN_TC_NODUP force a shape.
+int wn_tc_tile_utt(int B, int S)
 {
     if (getenv("NVWN_TC_NODUP")) return 128;
+    if (const char* v = getenv("NVWN_TC_TILE")) { const int t = atoi(v); if (t == 128 || t == 64 || (t == 32 && S == 256)) return t; }
+    if (S == 256 && B <= 32 * 64) return 32;
     return B <= 64 * 148 ? 64 : 128;
 }
 
 size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B)
 {
-    const int TU = wn_tc_tile_utt(B);
+    const int TU = wn_tc_tile_utt(B, S);
     return (size_t)(maxDil + 1) * L * ((B + TU - 1) / TU) * TILE;
 }
 
-size_t wn_tc_cond_bytes(int L, int B, int N) { return (size_t)N * L * cond_bpad(B, wn_tc_tile_utt(B)) * 256; }
+size_t wn_tc_cond_bytes(int S, int L, int B, int N) { return (size_t)N * L * cond_bpad(B, wn_tc_tile_utt(B, S)) * 256; }
 
-cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream)
+cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream)
 {
     if (nsamples <= 0) return cudaSuccess;
     const size_t total = (size_t)nsamples * L * B * 16;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    tc_cond_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<unsigned char*>(dst), src_dev, first_sample, nsamples, L, B, wn_tc_tile_utt(B));
+    tc_cond_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<unsigned char*>(dst), src_dev, first_sample, nsamples, L, B, wn_tc_tile_utt(B, S));
     return cudaGetLastError();
 }
 
@@ -1216,15 +1231,16 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t 
     const int nstage = pick_nstage(p.S, p.L);
     if (nstage < 3) return cudaErrorInvalidValue;
     const size_t smem = tc_smem_bytes(p.S, p.L, nstage);
-    const int TU = wn_tc_tile_utt(p.B);
+    const int TU = wn_tc_tile_utt(p.B, p.S);
     const int grid = (p.B + TU - 1) / TU;
     cudaError_t e = cudaErrorInvalidValue;
-    const bool dup = TU == 64;                                  // tiles of at most 64 utterances: 4 threads per utterance
+    const int cp = 128 / TU;                                    // row copies per utterance: 2 cp threads work for each
     const unsigned char* im8 = static_cast<const unsigned char*>(tc_image_);
     // Fused schedule (one MMA<->epilogue round trip per layer, +1 weight chunk per layer) while the launch is latency-bound;
     // with (nearly) every SM streaming the weights from L2 the extra chunk costs more than the round trip saves
     // (measured, 64-utterance tiles: 2048 utt. 50.9M vs 44.5M samples/s fused; 9472 utt. 175.6M fused vs 196.4M unfused).
-    static const int fused_env = []() { const char* v = getenv("NVWN_TC_FUSED"); return v ? (v[0] == '0' ? 0 : 1) : -1; }();
+    const char* fv = getenv("NVWN_TC_FUSED");                   // "0" / "1" force a schedule (tests)
+    const int fused_env = fv ? (fv[0] == '0' ? 0 : 1) : -1;
     const bool fused = fused_env >= 0 ? fused_env == 1 : !(TU == 64 && grid > 96);
 #define WN_TC_LAUNCH(SV, DV, FV)                                                                                     \
     do {                                                                                                             \
@@ -1233,10 +1249,15 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t 
         wn_tc_kernel<SV, DV, FV><<<grid, NT, smem, stream>>>(p, im8, nstage);                                       \
     } while (0)
 #define WN_TC_LAUNCH2(SV, DV) do { if (fused) WN_TC_LAUNCH(SV, DV, true); else WN_TC_LAUNCH(SV, DV, false); } while (0)
-    if (p.S == 256) { if (dup) WN_TC_LAUNCH2(256, true); else WN_TC_LAUNCH2(256, false); }
-    else { if (dup) WN_TC_LAUNCH2(128, true); else WN_TC_LAUNCH2(128, false); }
+    if (p.S == 256) {
+        if (cp == 4) WN_TC_LAUNCH(256, 4, true);                // 32-utterance tiles exist for the fused schedule only
+        else if (cp == 2) WN_TC_LAUNCH2(256, 2);
+        else WN_TC_LAUNCH2(256, 1);
+    } else {
+        if (cp == 2) WN_TC_LAUNCH2(128, 2); else WN_TC_LAUNCH2(128, 1);
+    }
 #undef WN_TC_LAUNCH2
 #undef WN_TC_LAUNCH
-    if (info) { info->kernel = 17; info->grid = grid; info->block = NT; info->smem_bytes = (int)smem; info->batch_per_cta = dup ? 64 : 128; info->cluster = 1; }
+    if (info) { info->kernel = 17; info->grid = grid; info->block = NT; info->smem_bytes = (int)smem; info->batch_per_cta = TU; info->cluster = 1; }
     return cudaGetLastError();
 }

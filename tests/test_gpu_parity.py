@@ -159,7 +159,7 @@ def _logit_check(za_o, za_g, rel=1e-2, mean_rel=None):
         assert (err / scale).mean() <= mean_rel, f"mean err / scale {(err / scale).mean()}"
 
 
-@pytest.mark.parametrize("kernel", ["stream", "auto", "tc_nodup"])
+@pytest.mark.parametrize("kernel", ["stream", "auto", "tc_tile64", "tc_tile64_unfused", "tc_nodup"])
 @pytest.mark.parametrize("shape", [
     (64, 256, 256, 20, 8, 24, 8),
     (64, 128, 256, 20, 4, 16, 4),
@@ -175,6 +175,12 @@ def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
         monkeypatch.setenv("NVWN_FP16_KERNEL", "stream")
     if kernel == "tc_nodup":                       # 128-utterance tiles, two threads per utterance (the large-batch variant)
         monkeypatch.setenv("NVWN_TC_NODUP", "1")
+    if kernel.startswith("tc_tile64"):             # 64-utterance tiles, four threads per utterance ("auto" picks 32-utterance
+        monkeypatch.setenv("NVWN_TC_TILE", "64")   # tiles, eight threads per utterance, at these batch sizes)
+    if kernel == "tc_tile64_unfused":              # the two-round-trip schedule that launches filling the GPU use
+        if B > 100:
+            pytest.skip("covered by the smaller shapes")
+        monkeypatch.setenv("NVWN_TC_FUSED", "0")
     w = refgen.lively_inputs(21 + B, R, S, A, L, B, N)
     # moderate the scales a little so that fp16 GEMM inputs stay well inside range
     o32 = cpu_oracle(w, L, B, N, R, S, A, md)
