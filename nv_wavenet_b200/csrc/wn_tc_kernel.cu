@@ -1,21 +1,23 @@
 // wn_tc_kernel.cu -- fp16 tensor-core kernel of the WaveNet inference loop (sm_100a: tcgen05 + TMEM + bulk TMA).
 //
-// ONE persistent CTA per tile of up to 128 utterances runs the whole autoregressive loop for `count` samples:
+// ONE persistent CTA (12 warps) per tile of 32 / 64 / 128 utterances runs the whole autoregressive loop for `count` samples:
 //
-//   warps 0-3  "epilogue": thread i owns utterance i of the tile (= TMEM lane i = row i of every activation tile).
-//              embed -> per layer: [D1 + Bh + Lh -> tanh * sigmoid -> h tile] [Dx + Bres + x -> x tile, history ring]
-//              -> relu(skip) tile -> relu(Zs) tile -> softmax + categorical sample, all thread-local
+//   warps 0-7  "epilogue": 2, 4 or 8 threads per utterance (an utterance occupies 1, 2 or 4 rows = TMEM lanes of every tile).
+//              embed -> per layer: [Dx + Bres + x -> x tile] [D1 + Lh + Bh -> tanh * sigmoid -> h tile]
+//              -> relu(skip) tile -> relu(Zs) tile -> softmax + categorical sample, all row-local
 //              (the reference spreads these over CTAs/threads: nv_wavenet_persistent.cuh:223-462, softmax.cuh:36-191).
-//   warp 4     lane 0: TMA producer.  Streams the pre-tiled fp16 weight image (and the x[t-d] history tiles) from
-//              L2 through an NSTAGE x 16 KB shared-memory ring with cp.async.bulk + mbarrier complete_tx.
-//   warp 5     lane 0: MMA issuer.  D[128 utterances x N channels] (fp32, TMEM) += X[128 x 64] . W[N x 64]^T with
-//              tcgen05.mma (activations = A operand, weights = B operand, both K-major SWIZZLE_128B);
-//              the skip accumulator lives in TMEM across all layers; tcgen05.commit signals the epilogue and
-//              frees ring stages.
+//   warp 8     TMA producer.  Streams the pre-tiled fp16 weight image (and the x[t-d] history tiles) from L2 through an
+//              NSTAGE x 16 KB shared-memory ring, and the conditioning tiles, with cp.async.bulk + mbarrier complete_tx.
+//   warp 9     MMA issuer A (and the only issuer of the unfused schedule): D[128 rows x N channels] (fp32, TMEM) +=
+//              X[128 x 64] . W[N x 64]^T with tcgen05.mma (activations = A operand, weights = B operand, both K-major
+//              SWIZZLE_128B); tcgen05.commit signals the epilogue and frees ring stages.
+//   warp 10    MMA issuer B of the fused schedule (skip and dilated-history GEMMs, half of the output GEMMs).
+//   warp 11    history copy of the fused schedule (x tile: shared -> global ring, one bulk copy).
 //
 // Replaces nv_wavenet_persistent.cuh + matrix_math.cuh + softmax.cuh of the reference for T_data = half.
 // Numerical contract (oracle/wavenet_oracle.c, WNO_PREC_FP16): weights, biases, embeddings, Lh and every GEMM
-// input rounded to fp16; fp32 accumulation; residual stream, skip sum, softmax in fp32.
+// input rounded to fp16; fp32 accumulation; residual stream, skip sum, softmax in fp32.  The fused schedule folds
+// Wcur_l . Wres_{l-1} into one fp16 matrix (see the kernel) -- same tolerance, checked by the same tests.
 #include "wn_common.h"
 #include "wn_math.cuh"
 #include "wn_sm100.cuh"
