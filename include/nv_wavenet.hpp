@@ -71,6 +71,12 @@ public:
     void getZa(float* hZa) { NVWN_CHK(nvwn_get_za(m_engine, hZa)); }
     void getP(float* hP) { NVWN_CHK(nvwn_get_p(m_engine, hP)); }
     void getYOut(int* yOut, int offset, int size, cudaStream_t stream = 0) { NVWN_CHK(nvwn_get_yout(m_engine, yOut, offset, size, stream)); }
+    /* Not in the reference class: mu-law decoded audio of yOut[b][offset .. offset+size) for every b, on the device
+     * (replaces the host post-processing of pytorch/nv_wavenet_inference.py:55-60); see nvwn_get_audio. */
+    void getAudio(float* audio_f32, short* audio_i16, int offset, int size, bool saturate = false, cudaStream_t stream = 0)
+    {
+        NVWN_CHK(nvwn_get_audio(m_engine, audio_f32, audio_i16, offset, size, saturate ? 1 : 0, stream));
+    }
 
     /* Chunked generation with overlapped device->host copies of finished chunks (nv_wavenet.cuh:445-497).
      * consume(yOut, initSample, count) is called per chunk once its copy has landed. */

@@ -63,6 +63,17 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
 int nvwn_run(nvwn_engine* e, int num_samples, int batch_size, int* yOut, int dump_activations, void* stream);
 /* nv_wavenet.cuh:439-444: 2-D copy of yOut[b][offset .. offset+size) for every b */
 int nvwn_get_yout(nvwn_engine* e, int* yOut, int offset, int size, void* stream);
+/* Output side: replaces the host post-processing of pytorch/nv_wavenet_inference.py:55-60 --
+ * utils.mu_law_decode_numpy (pytorch/utils.py:62-70) with mu_quantization = A, then MAX_WAV_VALUE * audio and
+ * astype('int16') -- on the device, straight from the engine's yOut: audio[b][j] for j in [0, size) decodes
+ * yOut[b][offset + j].  audio_f32 (in [-1, 1]) and / or audio_i16 may be NULL; each is [B][size], host or device memory
+ * (device destinations are filled asynchronously on `stream`).  Table-driven, the table computed on the host in double
+ * exactly as numpy does, so values equal the reference's.  saturate = 0 keeps the reference's cast (code A-1 decodes to
+ * +1.0 -> 32768 -> wraps to -32768), saturate = 1 clamps to 32767. */
+int nvwn_get_audio(nvwn_engine* e, float* audio_f32, short* audio_i16, int offset, int size, int saturate, void* stream);
+/* The decode table itself (host only, needs no GPU): entry x = decoded value of code x for mu_quantization = A; any of
+ * the three outputs (A entries each) may be NULL. */
+int nvwn_mulaw_table(int A, float* f32, short* i16_wrap, short* i16_saturate);
 
 /* last-sample activations [B][dim] as fp32 (nv_wavenet.cuh:424-438); valid after a run with dump=1 */
 int nvwn_get_xt_out(nvwn_engine* e, int layer, float* out);

@@ -18,6 +18,18 @@ __global__ void f32_to_f16_kernel(__half* __restrict__ dst, const float* __restr
     }
     for (size_t j = n4 * 4 + i; j < n; j += stride) dst[j] = __float2half_rn(src[j]);
 }
+// mu-law decode of sampled indices, table-driven: out[b][j] = lut[yOut[b * N + offset + j]]
+__global__ void mulaw_decode_kernel(const int* __restrict__ y, int N, int offset, int size, size_t total, int A, const float* __restrict__ lut_f,
+                                    const short* __restrict__ lut_s, float* __restrict__ out_f, short* __restrict__ out_s)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / (size_t)size, j = i % (size_t)size;
+        int v = y[b * (size_t)N + offset + j];
+        v = v < 0 ? 0 : (v >= A ? A - 1 : v);
+        if (out_f) out_f[i] = lut_f[v];
+        if (out_s) out_s[i] = lut_s[v];
+    }
+}
 __global__ void fill_int_kernel(int* dst, int v, size_t n)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
@@ -41,5 +53,16 @@ cudaError_t wn_fill_int(int* dst, int value, size_t n, cudaStream_t stream)
     size_t blocks = (n + 255) / 256;
     if (blocks > 1024) blocks = 1024;
     fill_int_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dst, value, n);
+    return cudaGetLastError();
+}
+
+cudaError_t wn_mulaw_decode(const int* yOut, int N, int offset, int size, int B, int A, const float* lut_f, const short* lut_s, float* out_f,
+                            short* out_s, cudaStream_t stream)
+{
+    const size_t total = (size_t)B * size;
+    if (total == 0) return cudaSuccess;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    mulaw_decode_kernel<<<(unsigned)blocks, 256, 0, stream>>>(yOut, N, offset, size, total, A, lut_f, lut_s, out_f, out_s);
     return cudaGetLastError();
 }

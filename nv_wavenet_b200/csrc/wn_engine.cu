@@ -10,6 +10,7 @@
 #include "../../include/nvwn_b200.h"
 #include "wn_common.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -17,6 +18,8 @@
 
 cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image, cudaStream_t stream, WnLaunchInfo* info);   // wn_tc_kernel.cu
 bool wn_tc_supported(int R, int S, int A, int L, int B);
+cudaError_t wn_mulaw_decode(const int* yOut, int N, int offset, int size, int B, int A, const float* lut_f, const short* lut_s, float* out_f,
+                            short* out_s, cudaStream_t stream);                                                  // wn_convert.cu
 size_t wn_tc_image_bytes(int R, int S, int A, int L);
 cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream);
 size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B);
@@ -75,6 +78,7 @@ struct nvwn_engine {
     bool tc_dirty = true;
     bool tc_mode = false;                    // decided once at creation: conditioning + history use the tiled layouts
 
+    float* lut_f = nullptr;                  // mu-law decode tables (nvwn_get_audio): A floats, then 2 x A int16 (wrap / saturate)
     unsigned long long* trace = nullptr;     // debug timeline (nvwn_debug_trace)
     int trace_t = -1;
 
@@ -240,7 +244,7 @@ int nvwn_destroy(nvwn_engine* e)
 {
     if (!e) return 0;
     void* ptrs[] = {e->blob, e->Lh, e->sel, e->forced, e->yPrev, e->yCur, e->yOut, e->ring, e->xtOut, e->skipOut,
-                    e->Zs, e->Za, e->P, e->stage_dev, e->tc_image, e->trace};
+                    e->Zs, e->Za, e->P, e->stage_dev, e->tc_image, e->trace, e->lut_f};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete e;
     return 0;
@@ -420,6 +424,68 @@ int nvwn_get_skip_out(nvwn_engine* e, int layer, float* out)
 int nvwn_get_zs(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_zs: NULL") : download(out, e->Zs, (size_t)e->B * e->A); }
 int nvwn_get_za(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_za: NULL") : download(out, e->Za, (size_t)e->B * e->A); }
 int nvwn_get_p(nvwn_engine* e, float* out) { return (!e || !out) ? fail(NVWN_EINVAL, "nvwn_get_p: NULL") : download(out, e->P, (size_t)e->B * e->A); }
+
+// mu-law expansion of one code, exactly as the reference's post-processing does it in double precision
+// (pytorch/utils.py:62-70 mu_law_decode_numpy, called with mu_quantization = A by pytorch/nv_wavenet_inference.py:58):
+//   mu = A - 1;  signal = 2 (x / mu) - 1;  audio = sign(signal) (1 / mu) ((1 + mu)^|signal| - 1)
+static double mulaw_expand(int x, int A)
+{
+    const double mu = (double)A - 1.0;
+    const double signal = 2.0 * ((double)x / mu) - 1.0;
+    const double magnitude = (1.0 / mu) * (pow(1.0 + mu, fabs(signal)) - 1.0);
+    return signal > 0.0 ? magnitude : (signal < 0.0 ? -magnitude : 0.0);
+}
+
+int nvwn_mulaw_table(int A, float* f32, short* i16_wrap, short* i16_saturate)
+{
+    if (A < 2) return fail(NVWN_EINVAL, "nvwn_mulaw_table: A must be at least 2");
+    for (int x = 0; x < A; x++) {
+        const double a = mulaw_expand(x, A);
+        const long long iv = (long long)(32768.0 * a);                       // MAX_WAV_VALUE * audio, truncated (astype('int16'))
+        if (f32) f32[x] = (float)a;
+        if (i16_wrap) i16_wrap[x] = (short)(unsigned short)((unsigned long long)iv & 0xFFFFull);
+        if (i16_saturate) i16_saturate[x] = (short)(iv > 32767 ? 32767 : (iv < -32768 ? -32768 : iv));
+    }
+    return 0;
+}
+
+int nvwn_get_audio(nvwn_engine* e, float* audio_f32, short* audio_i16, int offset, int size, int saturate, void* stream)
+{
+    if (!e || (!audio_f32 && !audio_i16)) return fail(NVWN_EINVAL, "nvwn_get_audio: NULL argument");
+    if (offset < 0 || size < 0 || offset + size > e->N) return fail(NVWN_EINVAL, "nvwn_get_audio: range out of bounds");
+    if (size == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int A = e->A;
+    if (!e->lut_f) {
+        // tables: float[A] | int16[A] (the reference's cast: trunc, code A-1 -> 32768 wraps to -32768) | int16[A] (clamped)
+        std::vector<unsigned char> host((size_t)A * (sizeof(float) + 2 * sizeof(short)));
+        float* hf = reinterpret_cast<float*>(host.data());
+        short* hw = reinterpret_cast<short*>(host.data() + (size_t)A * sizeof(float));
+        nvwn_mulaw_table(A, hf, hw, hw + A);
+        CK(cudaMalloc((void**)&e->lut_f, host.size()));
+        CK(cudaMemcpy(e->lut_f, host.data(), host.size(), cudaMemcpyHostToDevice));
+    }
+    const short* lut_s = reinterpret_cast<const short*>(e->lut_f + A) + (saturate ? A : 0);
+    const size_t total = (size_t)e->B * size;
+    const bool f_dev = !audio_f32 || is_device_ptr(audio_f32), s_dev = !audio_i16 || is_device_ptr(audio_i16);
+    float* df = audio_f32;
+    short* ds = audio_i16;
+    void* tmp = nullptr;
+    if (!f_dev || !s_dev) {                                                   // host destination(s): decode into a device scratch, copy out
+        CK(cudaMalloc(&tmp, total * (sizeof(float) + sizeof(short))));
+        if (!f_dev) df = static_cast<float*>(tmp);
+        if (!s_dev) ds = reinterpret_cast<short*>(static_cast<char*>(tmp) + total * sizeof(float));
+    }
+    cudaError_t ce = wn_mulaw_decode(e->yOut, e->N, offset, size, e->B, A, e->lut_f, lut_s, df, ds, st);
+    if (ce == cudaSuccess && !f_dev) ce = cudaMemcpyAsync(audio_f32, df, total * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess && !s_dev) ce = cudaMemcpyAsync(audio_i16, ds, total * sizeof(short), cudaMemcpyDeviceToHost, st);
+    if (tmp) {
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        cudaFree(tmp);
+    }
+    if (ce != cudaSuccess) return fail((int)ce, std::string("nvwn_get_audio: ") + cudaGetErrorString(ce));
+    return 0;
+}
 
 // debug only (not part of the public ABI): record a clock64 timeline of sample `t` of block 0 into `out` (3 x 1024 words)
 int nvwn_debug_trace(nvwn_engine* e, int t, unsigned long long* out_host, int fetch)

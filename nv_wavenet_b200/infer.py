@@ -127,6 +127,26 @@ class NVWavenetInfer:
         p, k = _ptr(y_out, np.int32)
         check(self._l.nvwn_get_yout(self._h, p, offset, size, _stream(stream)), "getYOut")
 
+    def get_audio(self, offset=0, size=None, int16=False, saturate=False, out=None, stream=None):
+        """Device-side replacement of the reference's host post-processing (pytorch/nv_wavenet_inference.py:55-60):
+        mu-law decode (utils.mu_law_decode_numpy, mu_quantization = A) of yOut[:, offset:offset+size], as float32
+        in [-1, 1] or, with int16=True, as `(MAX_WAV_VALUE * audio).astype('int16')`.  `out`: numpy array or torch
+        tensor [B][size] of the matching dtype (a CUDA tensor is filled asynchronously on `stream`); allocated
+        (numpy) if None.  saturate=False keeps the reference's cast of the top code (+1.0 -> -32768)."""
+        size = self.N - offset if size is None else size
+        if out is None:
+            out = np.empty((self.B, size), np.int16 if int16 else np.float32)
+        if isinstance(out, np.ndarray):
+            assert out.flags["C_CONTIGUOUS"] and out.dtype == (np.int16 if int16 else np.float32) and out.size == self.B * size
+            p = C.c_void_p(out.ctypes.data)
+        else:                               # torch tensor
+            import torch
+            assert out.is_contiguous() and out.dtype == (torch.int16 if int16 else torch.float32) and out.numel() == self.B * size
+            p = C.c_void_p(out.data_ptr())
+        check(self._l.nvwn_get_audio(self._h, None if int16 else p, p if int16 else None, offset, size, int(saturate),
+                                     _stream(stream)), "getAudio")
+        return out
+
     # ---- run (nv_wavenet.cuh:445-639) ----
     def run_partial(self, init_sample, num_samples, batch_size, y_out=None, batch_size_per_block=1,
                     dump_activations=False, stream=None):
