@@ -46,6 +46,20 @@ int nvwn_set_inputs(nvwn_engine* e, const float* Lh, const float* selectors);
 /* extension: selectors only / conditioning only (conditioning may be uploaded in chunks of whole samples) */
 int nvwn_set_selectors(nvwn_engine* e, const float* selectors);
 int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int num_samples, void* stream);
+/* Conditioning producer on the device.  Replaces, for inference, WaveNet.get_cond_input
+ * (pytorch/wavenet.py:190-202: ConvTranspose1d(C, C, window, stride) upsampling trimmed by window - stride, then the
+ * 1x1 cond_layers convolution C -> L*2R) and the permutes to [N][L][B][2R] (pytorch/nv_wavenet.py:48-49,181):
+ *   features [B][C][T] (mel frames), upsample_weight [C][C][window] (torch ConvTranspose1d layout), upsample_bias [C],
+ *   cond_weight [L*2R][C] (Conv1d weight, kernel size 1), cond_bias [L*2R]; all fp32, host or device memory.
+ * Produces conditioning for samples [first_sample, first_sample + T*stride) in chunks, directly in the engine's
+ * conditioning store -- the [N][L][B][2R] fp32 tensor never exists.  Returns after the work has completed. */
+int nvwn_set_conditioning_from_features(nvwn_engine* e, const float* features, int n_cond_channels, int num_frames,
+                                        const float* upsample_weight, const float* upsample_bias, int window, int stride,
+                                        const float* cond_weight, const float* cond_bias, int first_sample, void* stream);
+/* The same arithmetic on the host (needs no GPU; test / reference use): Lh [T*stride][L][B][2R], host pointers. */
+int nvwn_cond_from_features_host(float* Lh, const float* features, int batch_size, int n_cond_channels, int num_frames,
+                                 const float* upsample_weight, const float* upsample_bias, int window, int stride,
+                                 const float* cond_weight, const float* cond_bias, int num_layers, int R);
 int nvwn_reset_history(nvwn_engine* e);
 /* extension (teacher forcing): forced[b*num_samples + t] is fed back instead of the sampled index;
  * NULL switches it off.  Copied. */

@@ -18,6 +18,11 @@
 
 cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image, cudaStream_t stream, WnLaunchInfo* info);   // wn_tc_kernel.cu
 bool wn_tc_supported(int R, int S, int A, int L, int B);
+cudaError_t wn_cond_transpose_wu(float* WuT, const float* Wu, int C, int K, cudaStream_t stream);              // wn_cond_producer.cu
+cudaError_t wn_cond_produce(float* out, float* U, const float* feat, const float* WuT, const float* bu, const float* Wc, const float* bc,
+                            int B, int C, int T, int K, int stride, int L, int R, int n0, int m, cudaStream_t stream);
+void wn_cond_host(float* Lh, const float* feat, const float* Wu, const float* bu, const float* Wc, const float* bc,
+                  int B, int C, int T, int K, int stride, int L, int R);
 cudaError_t wn_mulaw_decode(const int* yOut, int N, int offset, int size, int B, int A, const float* lut_f, const short* lut_s, float* out_f,
                             short* out_s, cudaStream_t stream);                                                  // wn_convert.cu
 size_t wn_tc_image_bytes(int R, int S, int A, int L);
@@ -292,6 +297,55 @@ int nvwn_set_out_weights(nvwn_engine* e, const float* Wzs, const float* Bzs, con
     e->tc_dirty = true;
     CK(cudaStreamSynchronize(0));
     return 0;
+}
+
+int nvwn_cond_from_features_host(float* Lh, const float* features, int batch_size, int n_cond_channels, int num_frames,
+                                 const float* upsample_weight, const float* upsample_bias, int window, int stride,
+                                 const float* cond_weight, const float* cond_bias, int num_layers, int R)
+{
+    if (!Lh || !features || !upsample_weight || !upsample_bias || !cond_weight || !cond_bias) return fail(NVWN_EINVAL, "nvwn_cond_from_features_host: NULL argument");
+    if (batch_size < 1 || n_cond_channels < 1 || num_frames < 1 || window < stride || stride < 1 || num_layers < 1 || R < 1)
+        return fail(NVWN_EINVAL, "nvwn_cond_from_features_host: bad sizes (need window >= stride >= 1)");
+    wn_cond_host(Lh, features, upsample_weight, upsample_bias, cond_weight, cond_bias, batch_size, n_cond_channels, num_frames, window, stride, num_layers, R);
+    return 0;
+}
+
+int nvwn_set_conditioning_from_features(nvwn_engine* e, const float* features, int n_cond_channels, int num_frames,
+                                        const float* upsample_weight, const float* upsample_bias, int window, int stride,
+                                        const float* cond_weight, const float* cond_bias, int first_sample, void* stream)
+{
+    if (!e || !features || !upsample_weight || !upsample_bias || !cond_weight || !cond_bias) return fail(NVWN_EINVAL, "nvwn_set_conditioning_from_features: NULL argument");
+    const int C = n_cond_channels, T = num_frames, K = window;
+    if (C < 1 || T < 1 || stride < 1 || K < stride) return fail(NVWN_EINVAL, "nvwn_set_conditioning_from_features: bad sizes (need window >= stride >= 1)");
+    const long long Nn = (long long)T * stride;
+    if (first_sample < 0 || first_sample + Nn > e->N) return fail(NVWN_EINVAL, "nvwn_set_conditioning_from_features: num_frames * stride samples do not fit the engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per = (size_t)e->L * e->B * 2 * e->R;                       // floats of conditioning per sample
+    // chunk of whole samples: ~64 MB of fp32 at a time
+    int chunk = (int)(((size_t)16 << 20) / per);
+    if (chunk < 1) chunk = 1;
+    if (chunk > Nn) chunk = (int)Nn;
+    const size_t n_feat = (size_t)e->B * C * T, n_wu = (size_t)C * C * K, n_wc = (size_t)e->L * 2 * e->R * C, n_bc = (size_t)e->L * 2 * e->R;
+    // one scratch allocation: features | Wu | WuT | bu | Wc | bc | U chunk | Lh chunk
+    const size_t floats = n_feat + 2 * n_wu + C + n_wc + n_bc + (size_t)e->B * chunk * C + (size_t)chunk * per;
+    float* scratch = nullptr;
+    CK(cudaMalloc((void**)&scratch, floats * sizeof(float)));
+    float* d_feat = scratch; float* d_wu = d_feat + n_feat; float* d_wut = d_wu + n_wu; float* d_bu = d_wut + n_wu;
+    float* d_wc = d_bu + C; float* d_bc = d_wc + n_wc; float* d_u = d_bc + n_bc; float* d_out = d_u + (size_t)e->B * chunk * C;
+    cudaError_t ce = cudaSuccess;
+    auto put = [&](float* dst, const float* src, size_t n) { if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDefault, st); };
+    put(d_feat, features, n_feat); put(d_wu, upsample_weight, n_wu); put(d_bu, upsample_bias, C); put(d_wc, cond_weight, n_wc); put(d_bc, cond_bias, n_bc);
+    if (ce == cudaSuccess) ce = wn_cond_transpose_wu(d_wut, d_wu, C, K, st);
+    int rc = 0;
+    for (long long done = 0; done < Nn && ce == cudaSuccess && rc == 0; done += chunk) {
+        const int m = (int)((Nn - done < chunk) ? Nn - done : chunk);
+        ce = wn_cond_produce(d_out, d_u, d_feat, d_wut, d_bu, d_wc, d_bc, e->B, C, T, K, stride, e->L, e->R, (int)done, m, st);
+        if (ce == cudaSuccess) rc = nvwn_set_conditioning(e, d_out, first_sample + (int)done, m, stream);      // device source: converted in place, stream-ordered
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);                   // the scratch is freed below
+    cudaFree(scratch);
+    if (ce != cudaSuccess) return fail((int)ce, std::string("nvwn_set_conditioning_from_features: ") + cudaGetErrorString(ce));
+    return rc;
 }
 
 int nvwn_reset_history(nvwn_engine* e)

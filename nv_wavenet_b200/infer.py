@@ -99,6 +99,21 @@ class NVWavenetInfer:
         check(self._l.nvwn_set_conditioning(self._h, a, first_sample, num_samples, _stream(stream)), "setConditioning")
         return k
 
+    def set_conditioning_from_features(self, features, upsample_weight, upsample_bias, cond_weight, cond_bias, stride,
+                                       first_sample=0, stream=None):
+        """Device-side WaveNet.get_cond_input (pytorch/wavenet.py:190-202) + the permutes of pytorch/nv_wavenet.py:48-49,181:
+        features [B][C][T], upsample_weight [C][C][window] (ConvTranspose1d), cond_weight [L*2R][C] (or [L*2R][C][1]),
+        numpy arrays or torch tensors (host or CUDA).  Fills conditioning for T*stride samples from `first_sample`."""
+        shp = lambda a: tuple(a.shape)
+        B, Cc, T = shp(features)
+        assert B == self.B and shp(upsample_weight)[:2] == (Cc, Cc) and shp(cond_weight)[:2] == (self.L * 2 * self.R, Cc)
+        window = shp(upsample_weight)[2]
+        f, k1 = _ptr(features, np.float32); wu, k2 = _ptr(upsample_weight, np.float32); bu, k3 = _ptr(upsample_bias, np.float32)
+        wc, k4 = _ptr(cond_weight, np.float32); bc, k5 = _ptr(cond_bias, np.float32)
+        check(self._l.nvwn_set_conditioning_from_features(self._h, f, Cc, T, wu, bu, window, stride, wc, bc, first_sample,
+                                                          _stream(stream)), "setConditioningFromFeatures")
+        return T * stride
+
     def reset_history(self):
         check(self._l.nvwn_reset_history(self._h), "resetHistory")
 
