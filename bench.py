@@ -181,7 +181,8 @@ def workload_config(args, batch):
                         f"batch {args.batch}/GPU ({batch} total) x {args.samples} samples",
             "batch_per_gpu": args.batch, "global_batch": batch, "samples_per_utterance": args.samples,
             "parallelism": f"batch-shard x{args.gpus} (no per-step collective)",
-            "l2_policy": "conditioning stream (>5 GB/step) exceeds L2; weights are L2/SMEM-resident by design"}
+            "l2_policy": "conditioning stream (>5 GB/step) exceeds L2; weights are L2/SMEM-resident by design",
+            **({"note": os.environ["NVWN_BENCH_NOTE"]} if os.environ.get("NVWN_BENCH_NOTE") else {})}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -376,7 +377,18 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_ours(args, rank, world, local_rank)
+    try:
+        run_ours(args, rank, world, local_rank)
+    except Exception as exc:  # noqa: BLE001
+        # A device-side failure (the kernel's bounded mbarrier waits trap instead of hanging) poisons the CUDA context.
+        # Single-process runs re-measure ONCE in a fresh process with the most exercised tile shape of the kernel and say
+        # so in config.note; anything else (multi-rank, second failure) is fatal.
+        if world == 1 and not os.environ.get("NVWN_BENCH_NOTE"):
+            print(f"bench.py: run failed ({type(exc).__name__}: {exc}); re-measuring once with NVWN_TC_TILE=64", file=sys.stderr, flush=True)
+            env = dict(os.environ, NVWN_TC_TILE="64",
+                       NVWN_BENCH_NOTE=f"re-measured with 64-utterance tiles after a failed first attempt ({type(exc).__name__})")
+            os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env)
+        raise
 
 
 if __name__ == "__main__":
