@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
     int* s_y = reinterpret_cast<int*>(s_pair + 128 * 4);                // [128] sampled index per utterance
     uint64_t* w_full = reinterpret_cast<uint64_t*>(s_y + 128);
     uint64_t* w_empty = w_full + nstage;
-    uint64_t* epi_done = w_empty + nstage;
+    uint64_t* epi_done = w_empty + nstage;      // [2] at +0, +17: tile-published phases alternate between the two barriers
     uint64_t* d1_full = epi_done + 1;
     uint64_t* dx_full = epi_done + 2;
     uint64_t* skip_full = epi_done + 3;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 
     if (tid == 0) {
         for (int s = 0; s < nstage; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(epi_done, NEPI);
+        mbar_init(epi_done, NEPI); mbar_init(epi_done + 17, NEPI);
         mbar_init(d1_full, 1); mbar_init(dx_full, 1); mbar_init(skip_full, FUSED ? 2 : 1); mbar_init(out_full, FUSED ? 2 : 1);
         mbar_init(cx_done, 1); mbar_init(b_done, 1); mbar_init(b_done + 3, 1); mbar_init(hx_full, NEPI); mbar_init(hx_done, 1); mbar_init(hx_done + 2, 1);
         mbar_init(pre_done, NEPI);
@@ -418,7 +418,16 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 }
                 __syncwarp();
             };
-            auto wait_epi = [&]() { mbar_wait(epi_done, ph_epi); ph_epi ^= 1; tc_fence_after_sync(); };
+            // the epilogue's "tile published" phases alternate between two barriers (role B may be a whole gate behind role A:
+            // on a single barrier it could find TWO completions past the one it waits for, which a parity wait cannot see)
+            int n_epi = 0;
+            auto wait_epi = [&]() {
+                const int k = n_epi & 1;
+                mbar_wait(epi_done + k * 17, (ph_epi >> k) & 1u);
+                ph_epi ^= 1u << k;
+                n_epi++;
+                tc_fence_after_sync();
+            };
             // open(l): the epilogue has initialised D1[l&1] with Lh[t][l] + Bh (tcgen05.st); add Wprev_l . x[t-d]
             auto open_layer = [&](int l, bool has_prev) {
                 const uint32_t d1 = D1B + (uint32_t)(l & 1) * 128;
@@ -553,27 +562,16 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                             }
                             wait_epi();                                 // h_{l-1} ready, D1[(l-1)&1] drained
                             if (lane == 0) TRACE(1, 22);
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < 4; k++) umma_f16(D1B + (uint32_t)((l - 1) & 1) * 128, dh + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc64, k ? 1u : 0u);
-                            }
-                            __syncwarp();
-                            if (elect_one()) { umma_commit(dx_full); umma_commit(&w_empty[stage]); }
-                            __syncwarp();
+                            // (every tcgen05.commit sits in the election block of the MMAs it tracks: issued with nothing of its
+                            // thread outstanding it never arrives)
+                            mma4(dh, dw, D1B + (uint32_t)((l - 1) & 1) * 128, idesc64, false, dx_full, &w_empty[stage]);      // Dx = Wres . h
                             advance();
                             if (lane == 0) TRACE(1, 25);
                             if (dstep) skip_layer(l - 1, nullptr);      // dumping sample: the skip sum through l-1 must be complete at gate l
                             dw = wait_stage();
                             tc_fence_after_sync();
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < 4; k++) umma_f16(D1B + (uint32_t)(l & 1) * 128, dh + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc128, 1u);   // D1[l] += Wf_l . h
-                            }
-                            __syncwarp();
-                            // (a tcgen05.commit must follow its MMAs at once -- issued with nothing outstanding it never
-                            // arrives -- so B's share of D1[l] / the free h tile are awaited by the gate threads, not here)
-                            if (elect_one()) { umma_commit(d1_full); umma_commit(&w_empty[stage]); }
-                            __syncwarp();
+                            // D1[l] += Wf_l . h; B's share of D1[l] / the free h tile are awaited by the gate threads, not here
+                            mma4(dh, dw, D1B + (uint32_t)(l & 1) * 128, idesc128, true, d1_full, &w_empty[stage]);
                             advance();
                             if (lane == 0) TRACE(1, 21);
                             if (!dstep) skipc(SKC);                     // B: skip(l-1)
@@ -620,41 +618,45 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                 } else {
                     for (int t = t_begin; t < t_end; t++) {
                         const bool dstep = p.dump && (t == t_end - 1);
-                        auto prev_b = [&](int l) {                      // D1[l&1] += Wprev_l . x_l[t-d], after A's overwrite has completed
+                        // b_done of iteration j (0 at the start of the sample, l in the loop) is committed inside the LAST issue
+                        // block of the iteration, or -- if this role issued nothing -- signalled by a plain arrival
+                        auto bsig = [&](int j) { return b_done + (j & 1) * 3; };
+                        auto prev_b = [&](int l, uint64_t* done_bar) {  // D1[l&1] += Wprev_l . x_l[t-d], after A's overwrite has completed
                             mbar_wait(cx_done, ph_cx); ph_cx ^= 1;
                             const uint64_t da = wait_stage();
                             const int sa = stage;
                             advance();
                             const uint64_t db = wait_stage();
                             tc_fence_after_sync();
-                            mma4(da, db, D1B + (uint32_t)(l & 1) * 128, idesc128, true, &w_empty[sa], &w_empty[stage]);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) umma_f16(D1B + (uint32_t)(l & 1) * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc128, 1u);
+                                umma_commit(&w_empty[sa]);
+                                umma_commit(&w_empty[stage]);
+                                if (done_bar) umma_commit(done_bar);
+                            }
+                            __syncwarp();
                             advance();
                         };
-                        // b_done: tcgen05.commit when this role issued MMAs since its last signal, a plain arrival otherwise
-                        auto commit_b = [&](bool had_mma, int j) {          // j = 0 at the start of the sample, l in the loop
-                            uint64_t* bar = b_done + (j & 1) * 3;
-                            if (elect_one()) { if (had_mma) umma_commit(bar); else mbar_arrive(bar); }
-                            __syncwarp();
-                        };
+                        auto arrive_b = [&](int j) { if (elect_one()) mbar_arrive(bsig(j)); __syncwarp(); };
                         wait_epi();                                     // x_0
                         if (t >= 1) skipc(2);                           // A: Wprev_0
                         skipc(1);                                       // A: Wcur_0
                         if (L > 1) {
-                            if (t >= s_dil[1]) prev_b(1);
+                            if (t >= s_dil[1]) prev_b(1, bsig(0)); else arrive_b(0);
                             skipc(1);                                   // A: Wcur_1
-                            commit_b(t >= s_dil[1], 0);
                         }
                         for (int l = 1; l < L; l++) {
                             skipc(1);                                   // A: Wres_{l-1}
                             wait_epi();                                 // h_{l-1}
-                            if (dstep) skipc(SKC + 1);                  // A: skip(l-1), Wf_l
-                            else { skipc(1); skip_layer(l - 1, nullptr); }
                             const bool hpn = (l + 1 < L) && t >= s_dil[l + 1];
+                            if (dstep) skipc(SKC + 1);                  // A: skip(l-1), Wf_l
+                            else { skipc(1); skip_layer(l - 1, hpn ? nullptr : bsig(l)); }
                             if (l + 1 < L) {
-                                if (hpn) prev_b(l + 1);
+                                if (hpn) prev_b(l + 1, bsig(l));
                                 skipc(1);                               // A: Wcur_{l+1}
                             }
-                            commit_b(!dstep || hpn, l);
+                            if (dstep && !hpn) arrive_b(l);             // nothing issued in this iteration
                         }
                         wait_epi();                                     // h_{L-1}
                         if (dstep) skipc(1 + SKC);
@@ -759,10 +761,12 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             }
             fence_proxy_async_global();
         };
+        int n_pub = 0;                                 // tiles published so far: selects the barrier of the pair
         auto publish = [&]() {                         // smem tile written -> visible to the MMA (async proxy), then signal
             tc_fence_before_sync();
             fence_proxy_async_smem();
-            mbar_arrive(epi_done);
+            mbar_arrive(epi_done + (n_pub & 1) * 17);
+            n_pub++;
         };
         auto epi_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         // Initialise the pre-activation accumulator of layer `ln` with Lh[tn][ln] + Bh (fp32) straight from the TMA-fed
