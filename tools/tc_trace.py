@@ -23,10 +23,10 @@ assert lib.nvwn_debug_trace(e._h, T | (TID << 16), None, 0) == 0
 e.run(N, B, None); torch.cuda.synchronize()
 buf = np.zeros(3 * 1024, np.uint64)
 assert lib.nvwn_debug_trace(e._h, T, buf.ctypes.data, 1) == 0
-names = {28: "mma: hist waited", 26: "mma: res mmas issued", 29: "mma: Wf stage ready", 32: "mma: open_f done", 33: "mma: curx stage ready", 34: "mma: curx issued", 13: "E2 done", 14: "cond seen", 15: "prestore st done", 16: "gate ld done", 5: "cond loaded", 25: "mma: res issued(F)", 30: " E1 ld0 done", 31: " E1 half0 done", 32: " E1 ld1 done", 33: " E1 half1 done", 40: " E2 ld0 done", 41: " E2 half0 done",
-         42: " E2 ld1 done", 43: " E2 half1 done", 1: "x0 arrive", 2: "D1 full seen", 12: "E1 math done", 3: "h arrive", 4: "Dx full seen", 5: "x arrive", 6: "skip full seen",
-         7: "skq arrive", 9: "zsq arrive", 10: "Dza seen", 11: "sample done", 20: "mma: x seen", 21: "mma: cur issued",
-         22: "mma: h seen", 23: "mma: res issued", 24: "mma: layer issued"}
+names = {1: "x0 published", 14: "cond tile landed", 5: "cond in registers", 4: "Dx full seen", 13: "x tile published (E2 done)",
+         2: "D1 full seen", 16: "gate: TMEM read done", 12: "gate: math done", 3: "h published", 6: "skip full seen",
+         7: "relu(skip) published", 9: "relu(Zs) published", 10: "Dza seen", 11: "sample done", 15: "prestore st done",
+         20: "A: x0 seen", 22: "A: h seen", 25: "A: res issued", 21: "A: Wf issued", 23: "issuer: skip issued", 24: "A: layer issued"}
 ev = []
 for role in range(3):
     for v in buf[role * 1024:(role + 1) * 1024]:
