@@ -30,25 +30,27 @@
 extern "C" {
 #endif
 
-void wavenet_infer(int sample_count,
-                   int batch_size,
-                   float* embedding_prev,
-                   float* embedding_curr,
-                   int num_layers,
+/* Argument order and types are the ABI (pytorch/wavenet_infer.h:34-52); the reference's parameter names are given in
+ * the comments.  L = n_layers; every matrix fp32 column-major. */
+void wavenet_infer(int n_samples,                 /* sample_count */
+                   int n_utterances,              /* batch_size */
+                   float* emb_prev,               /* embedding_prev  [A][R] */
+                   float* emb_cur,                /* embedding_curr  [A][R] */
+                   int n_layers,                  /* num_layers */
                    int max_dilation,
-                   float** in_layer_weights_prev,
-                   float** in_layer_weights_curr,
-                   float** in_layer_biases,
-                   float** res_layer_weights,
-                   float** res_layer_biases,
-                   float** skip_layer_weights,
-                   float** skip_layer_biases,
-                   float* conv_out_weight,
-                   float* conv_end_weight,
-                   int use_embed_tanh,
-                   float* cond_input,
+                   float** w_prev,                /* in_layer_weights_prev  L x (2R x R), the x[t-d] half of the dilated conv */
+                   float** w_cur,                 /* in_layer_weights_curr  L x (2R x R), the x[t] half */
+                   float** b_gate,                /* in_layer_biases        L x 2R */
+                   float** w_res,                 /* res_layer_weights      L x (R x R) */
+                   float** b_res,                 /* res_layer_biases       L x R */
+                   float** w_skip,                /* skip_layer_weights     L x (S x R) */
+                   float** b_skip,                /* skip_layer_biases      L x S */
+                   float* w_zs,                   /* conv_out_weight        A x S */
+                   float* w_za,                   /* conv_end_weight        A x A */
+                   int tanh_on_embedding,         /* use_embed_tanh */
+                   float* conditioning,           /* cond_input  [n_samples][L][n_utterances][2R] */
                    int implementation,
-                   int* samples);
+                   int* samples_out);             /* samples     [n_utterances][n_samples] */
 
 /* channel counts of this build (pytorch/wavenet_infer.h:54-57) */
 int get_R(void);
