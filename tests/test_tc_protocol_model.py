@@ -63,3 +63,14 @@ def test_model_sees_phase_aliasing_on_a_single_tile_published_barrier():
     assert h is None or "aliasing" in h or "deadlock" in h
     hs = [_first_hazard("one_epi_done", 60, L=20, S=128, steps=3, dil=[1] * 20, dump_last=True, t0=1, slow={"B": 8})]
     assert any(x and ("aliasing" in x or "deadlock" in x) for x in hs)
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_unfused_schedule_completes_without_hazard(seed):
+    rng = random.Random(1000 + seed)
+    L = rng.choice([1, 2, 3, 5, 20])
+    kw = dict(L=L, S=rng.choice([128, 256]), NC=rng.choice([1, 2]), nstage=rng.choice([3, 4, 6, 8]), steps=rng.choice([2, 3]),
+              dil=dilations(L, rng.choice([1, 2, 8, 512])), t0=rng.choice([0, 1, 7, 600]),
+              slow=rng.choice([None, {"A": 4.0}, {"E": 3.0}, {"P": 6.0}, {"E": 0.3}]))
+    sim = M.trial(seed, schedule="unfused", **kw)
+    assert {"P", "A"} <= sim.finished

@@ -507,9 +507,155 @@ def build(sim):
         sim.spawn(f"E#{wi}", epilogue(wi))
 
 
-def trial(seed, **kw):
+def build_unfused(sim):
+    """The two-round-trip schedule (single issuer, conditioning pre-stored into the accumulator by the epilogue):
+    what launches that fill the GPU use.  skip_full / out_full have ONE arrival here."""
+    L, SKC, nstage, NC = sim.L, sim.SKC, sim.nstage, sim.NC
+    dil = sim.dil
+    T = range(sim.t0, sim.t0 + sim.steps)
+    sim.skip_full.count = sim.skip_full.pending = 1
+    sim.out_full.count = sim.out_full.pending = 1
+
+    def producer():
+        stage, lap, g_cond = 0, 0, 0
+        for t in T:
+            def put(tag):
+                nonlocal stage, lap
+                if lap > 0:
+                    yield ("wait", sim.w_empty[stage], lap - 1)
+                s = stage
+                def land(s=s, tag=tag):
+                    sim.stage_content[s] = tag
+                    sim.w_full[s].arrive()
+                sim.at(sim.now + sim.lat("P", 300, 1200), land)
+                stage += 1
+                if stage == nstage: stage, lap = 0, lap + 1
+                yield ("delay", sim.lat("P", 30, 80))
+            def put_cond():
+                nonlocal g_cond
+                cb, k = g_cond % NC, g_cond // NC
+                if k > 0:
+                    yield ("wait", sim.cond_empty[cb], k - 1)
+                sim.at(sim.now + sim.lat("P", 400, 1500), sim.cond_full[cb].arrive)
+                g_cond += 1
+                yield ("delay", 40)
+            def put_prev(l):
+                if t >= dil[l]:
+                    yield from put(("pa", l)); yield from put(("pw", l))
+            yield from put_cond()
+            yield from put_prev(0)
+            for l in range(L):
+                if l + 1 < L: yield from put_cond()
+                yield from put(("cur", l))
+                if l > 0:
+                    for c in range(SKC): yield from put(("skip", l - 1, c))
+                yield from put(("res", l))
+                if l + 1 < L: yield from put_prev(l + 1)
+            for c in range(SKC): yield from put(("skip", L - 1, c))
+            for g in range(2):
+                for kt in range(sim.KT[g]):
+                    for nh in range(2): yield from put(("out", g, kt, nh))
+
+    def issuer():
+        stage, lap = 0, 0
+        k_epi = k_pre = 0
+        def take(tag):
+            nonlocal stage, lap
+            yield ("wait", sim.w_full[stage], lap)
+            got = sim.stage_content[stage]
+            if got[:len(tag)] != tag:
+                raise Hazard(f"issuer: expected chunk {tag} in stage {stage}, found {got}")
+            s = stage
+            stage += 1
+            if stage == nstage: stage, lap = 0, lap + 1
+            return s
+        def wait_epi():
+            nonlocal k_epi
+            yield ("wait", sim.epi_done[k_epi & 1], k_epi // 2); k_epi += 1
+        def group(n, reads, bars):
+            yield ("delay", sim.lat("A", 150, 300))
+            sim.mma("A", n, reads=reads)
+            for b in bars: sim.commit("A", b, b.name)
+            yield ("delay", sim.lat("A", 40, 100))
+        def open_layer(l, has_prev):
+            nonlocal k_pre
+            yield ("wait", sim.pre_done, k_pre); k_pre += 1
+            if has_prev:
+                sa = yield from take(("pa", l)); sb = yield from take(("pw", l))
+                yield from group(4, [("ring", sa), ("ring", sb)], [sim.w_empty[sa], sim.w_empty[sb]])
+        def skip_layer(l, done):
+            sts = []
+            for c in range(SKC): sts.append((yield from take(("skip", l, c))))
+            yield from group(4 * SKC, [("H", l & 1)] + [("ring", x) for x in sts], [sim.w_empty[x] for x in sts] + ([done] if done else []))
+        for t in T:
+            for l in range(L):
+                s = None
+                if l > 0: s = yield from take(("cur", l))
+                yield from wait_epi()                                   # x_l
+                if l == 0:
+                    yield from open_layer(0, t >= 1)
+                    s = yield from take(("cur", 0))
+                yield from group(4, [("X", 0), ("ring", s)], [sim.d1_full, sim.w_empty[s]])
+                if l > 0: yield from skip_layer(l - 1, None)
+                s = yield from take(("res", l))
+                yield from wait_epi()                                   # h_l
+                yield from group(4, [("H", l & 1), ("ring", s)], [sim.dx_full, sim.w_empty[s]])
+                if l + 1 < L: yield from open_layer(l + 1, t >= dil[l + 1])
+            yield from skip_layer(L - 1, sim.skip_full)
+            for g in range(2):
+                yield from wait_epi()
+                for kt in range(sim.KT[g]):
+                    for nh in range(2):
+                        s = yield from take(("out", g, kt, nh))
+                        last = kt == sim.KT[g] - 1 and nh == 1
+                        yield from group(4, [("BIG", kt), ("ring", s)], [sim.w_empty[s]] + ([sim.out_full] if last else []))
+
+    def epilogue(wi):
+        name = f"E#{wi}"
+        k_d1 = k_dx = k_skip = k_out = 0
+        g_pre = n_pub = 0
+        def publish():
+            nonlocal n_pub
+            sim.epi_done[n_pub & 1].arrive(); n_pub += 1
+        def prestore():
+            nonlocal g_pre
+            cb, k = g_pre % NC, g_pre // NC
+            yield ("wait", sim.cond_full[cb], k)
+            yield ("delay", sim.lat(name, 150, 500))
+            sim.cond_empty[cb].arrive(); sim.pre_done.arrive(); g_pre += 1
+        for t in T:
+            yield from prestore()
+            yield ("delay", sim.lat(name, 200, 500))                    # embedding
+            sim.write_ok(name, ("X", 0)); publish()
+            for l in range(L):
+                yield ("wait", sim.d1_full, k_d1); k_d1 += 1
+                yield ("delay", sim.lat(name, 300, 800))
+                sim.write_ok(name, ("H", l & 1)); publish()             # h_l
+                if l + 1 < L: yield from prestore()
+                yield ("wait", sim.dx_full, k_dx); k_dx += 1
+                yield ("delay", sim.lat(name, 250, 600))
+                if l + 1 < L:
+                    sim.write_ok(name, ("X", 0)); publish()             # x_{l+1}
+            yield ("wait", sim.skip_full, k_skip); k_skip += 1
+            yield ("delay", sim.lat(name, 800, 1600))
+            for r in [("X", 0), ("H", 0), ("H", 1)]: sim.write_ok(name, r)
+            publish()
+            yield ("wait", sim.out_full, k_out); k_out += 1
+            yield ("delay", sim.lat(name, 800, 1600))
+            for kt in range(4): sim.write_ok(name, ("BIG", kt))
+            publish()
+            yield ("wait", sim.out_full, k_out); k_out += 1
+            yield ("delay", sim.lat(name, 2000, 4000))
+
+    sim.spawn("P", producer())
+    sim.spawn("A", issuer())
+    for wi in range(sim.NE):
+        sim.spawn(f"E#{wi}", epilogue(wi))
+
+
+def trial(seed, schedule="fused", **kw):
     sim = Sim(seed=seed, **kw)
-    build(sim)
+    (build if schedule == "fused" else build_unfused)(sim)
     sim.run()
     return sim
 
