@@ -27,7 +27,7 @@ typedef struct nvwn_engine nvwn_engine;
 enum { NVWN_FP32 = 0, NVWN_FP16 = 1 };          /* T_data=float / T_data=half of the reference */
 enum { NVWN_EINVAL = -1, NVWN_EUNSUPPORTED = -2, NVWN_ENOMEM = -3 };
 /* kernel selection; the reference's Implementation enum values 0..4 are accepted and map to AUTO */
-enum { NVWN_KERNEL_AUTO = 0, NVWN_KERNEL_STREAM = 16, NVWN_KERNEL_TENSORCORE = 17 };
+enum { NVWN_KERNEL_AUTO = 0, NVWN_KERNEL_STREAM = 16, NVWN_KERNEL_TENSORCORE = 17, NVWN_KERNEL_LATENCY = 18 };
 
 /* nvWavenetInfer::nvWavenetInfer (nv_wavenet.cuh:311) */
 int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layers, int max_dilation,
@@ -98,7 +98,7 @@ int nvwn_get_p(nvwn_engine* e, float* out);
 
 /* introspection: what the last launch used */
 typedef struct {
-    int kernel;            /* NVWN_KERNEL_STREAM / NVWN_KERNEL_TENSORCORE */
+    int kernel;            /* NVWN_KERNEL_STREAM / NVWN_KERNEL_TENSORCORE / NVWN_KERNEL_LATENCY */
     int grid, block, smem_bytes, batch_per_cta, cluster;
     unsigned long long launches;        /* kernel launches issued by this engine so far */
     unsigned long long weight_bytes;    /* algorithmic weight+bias bytes per utterance-sample */

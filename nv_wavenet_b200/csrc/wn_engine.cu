@@ -30,6 +30,14 @@ cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream);
 size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B);
 size_t wn_tc_cond_bytes(int S, int L, int B, int N);
 cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream);
+// latency-mode fp16 kernel (wn_lat_kernel.cu)
+bool wn_lat_supported(int R, int S, int A, int L);
+size_t wn_lat_image_bytes(int S, int L);
+size_t wn_lat_ring_bytes(int L, int maxDil, int B);
+size_t wn_lat_cond_bytes(int L, int B, int N);
+cudaError_t wn_lat_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
+cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream);
+cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, cudaStream_t stream, WnLaunchInfo* info);
 
 namespace {
 
@@ -82,6 +90,7 @@ struct nvwn_engine {
     void* tc_image = nullptr;                // tensor-core kernel's pre-tiled weight image
     bool tc_dirty = true;
     bool tc_mode = false;                    // decided once at creation: conditioning + history use the tiled layouts
+    bool lat_mode = false;                   // decided once at creation: latency-mode kernel (fragment-ordered layouts); tc_image holds its weight image
 
     float* lut_f = nullptr;                  // mu-law decode tables (nvwn_get_audio): A floats, then 2 x A int16 (wrap / saturate)
     unsigned long long* trace = nullptr;     // debug timeline (nvwn_debug_trace)
@@ -125,14 +134,26 @@ int download(float* dst, const float* src, size_t n)
     return 0;
 }
 
-bool decide_tc(int dtype, int impl, int R, int S, int A, int L, int B)
+// fp16 kernel choice, made ONCE per engine (the layouts of the conditioning store and of the history ring depend on it):
+// 0 = stream, 1 = tensor-core (tcgen05, throughput mode), 2 = latency mode (mma.sync, register-resident chain).
+// `impl` NVWN_KERNEL_* forces a kernel; the environment variable NVWN_FP16_KERNEL = stream | tc | lat overrides AUTO (tests).
+int decide_fp16_kernel(int dtype, int impl, int R, int S, int A, int L, int B)
 {
-    if (dtype != NVWN_FP16) return false;
-    if (impl == NVWN_KERNEL_STREAM) return false;
+    if (dtype != NVWN_FP16) return 0;
+    if (impl == NVWN_KERNEL_STREAM) return 0;
+    const bool tc_ok = wn_tc_supported(R, S, A, L, B), lat_ok = wn_lat_supported(R, S, A, L);
+    if (impl == NVWN_KERNEL_TENSORCORE) return tc_ok ? 1 : 0;
+    if (impl == NVWN_KERNEL_LATENCY) return lat_ok ? 2 : 0;
     if (const char* env = getenv("NVWN_FP16_KERNEL")) {
-        if (!strcmp(env, "stream")) return false;
+        if (!strcmp(env, "stream")) return 0;
+        if (!strcmp(env, "tc")) return tc_ok ? 1 : 0;
+        if (!strcmp(env, "lat")) return lat_ok ? 2 : 0;
     }
-    return wn_tc_supported(R, S, A, L, B);
+    // one 16-utterance tile per SM: up to 148 x 16 utterances run as one wave of latency-mode CTAs
+    int lat_max = 148 * 16;
+    if (const char* env = getenv("NVWN_LAT_MAX_B")) lat_max = atoi(env);
+    if (lat_ok && B <= lat_max) return 2;
+    return tc_ok ? 1 : 0;
 }
 
 void fill_params(const nvwn_engine* e, WnParams& p, int init_sample, int count, int num_samples, int batch, int dump)
@@ -213,8 +234,12 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
         }                                                                                     \
     } while (0)
     ALLOC(e->blob, e->blob_bytes);
-    e->tc_mode = decide_tc(dtype, impl, R, S, A, num_layers, batch_size);
-    ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(S, num_layers, batch_size, num_samples) : Nz * L * Bz * 2 * R * td);
+    {
+        const int k = decide_fp16_kernel(dtype, impl, R, S, A, num_layers, batch_size);
+        e->tc_mode = k == 1; e->lat_mode = k == 2;
+    }
+    ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(S, num_layers, batch_size, num_samples)
+                 : e->lat_mode ? wn_lat_cond_bytes(num_layers, batch_size, num_samples) : Nz * L * Bz * 2 * R * td);
     ALLOC(e->sel, Nz * Bz * sizeof(float));
     ALLOC(e->forced, Nz * Bz * sizeof(int));
     ALLOC(e->yPrev, Bz * sizeof(int));
@@ -225,6 +250,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
         const size_t tcb = wn_tc_ring_bytes(S, num_layers, max_dilation, batch_size);     // tiled history layout of the tensor-core kernel
         if (tcb > ring_bytes) ring_bytes = tcb;
     }
+    if (e->lat_mode) ring_bytes = wn_lat_ring_bytes(num_layers, max_dilation, batch_size);
     ALLOC(e->ring, ring_bytes);
     ALLOC(e->xtOut, L * Bz * R * sizeof(float));
     ALLOC(e->skipOut, L * Bz * S * sizeof(float));
@@ -233,6 +259,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     ALLOC(e->P, Bz * A * sizeof(float));
     if (e->stage_elems) ALLOC(e->stage_dev, e->stage_elems * sizeof(float));
     if (e->tc_mode) ALLOC(e->tc_image, wn_tc_image_bytes(R, S, A, num_layers));
+    if (e->lat_mode) ALLOC(e->tc_image, wn_lat_image_bytes(S, num_layers));
 #undef ALLOC
     cudaMemsetAsync(e->blob, 0, e->blob_bytes, 0);
     cudaMemsetAsync(e->yOut, 0, Nz * Bz * sizeof(int), 0);
@@ -368,13 +395,17 @@ int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int
     if (!e || !Lh) return fail(NVWN_EINVAL, "nvwn_set_conditioning: NULL argument");
     if (first_sample < 0 || num_samples < 0 || first_sample + num_samples > e->N) return fail(NVWN_EINVAL, "nvwn_set_conditioning: sample range out of bounds");
     const size_t per = (size_t)e->L * e->B * 2 * e->R;
-    if (!e->tc_mode)
+    if (!e->tc_mode && !e->lat_mode)
         return upload(e, static_cast<char*>(e->Lh) + (size_t)first_sample * per * e->td, Lh, per * num_samples, (cudaStream_t)stream);
     // tensor-core layout: fp16, tiled per 128 utterances, 128-byte rows pre-swizzled so that TMA drops them straight into
     // an MMA operand tile (wn_tc_kernel.cu).  Host sources bounce through the staging buffer in whole samples.
     cudaStream_t st = (cudaStream_t)stream;
+    auto convert = [&](const float* src_dev, int first, int n) {
+        return e->lat_mode ? wn_lat_cond_convert(e->Lh, src_dev, first, n, e->L, e->B, st)
+                           : wn_tc_cond_convert(e->Lh, src_dev, first, n, e->S, e->L, e->B, st);
+    };
     if (is_device_ptr(Lh)) {
-        CK(wn_tc_cond_convert(e->Lh, Lh, first_sample, num_samples, e->S, e->L, e->B, st));
+        CK(convert(Lh, first_sample, num_samples));
         return 0;
     }
     const int chunk = (int)(e->stage_elems / per);
@@ -382,8 +413,9 @@ int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int
     for (int done = 0; done < num_samples; done += chunk) {
         const int m = (num_samples - done < chunk) ? num_samples - done : chunk;
         CK(cudaMemcpyAsync(e->stage_dev, Lh + (size_t)done * per, (size_t)m * per * sizeof(float), cudaMemcpyHostToDevice, st));
-        CK(wn_tc_cond_convert(e->Lh, e->stage_dev, first_sample + done, m, e->S, e->L, e->B, st));
+        CK(convert(e->stage_dev, first_sample + done, m));
     }
+    CK(cudaStreamSynchronize(st));      // host source: the header promises the data is copied before return
     return 0;
 }
 
@@ -433,7 +465,15 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
     WnParams p;
     fill_params(e, p, init_sample, count, num_samples, batch_size, dump_activations ? 1 : 0);
     if (count > 0) {
-        if (e->tc_mode) {
+        if (e->lat_mode) {
+            // a smaller batch_size runs the first batch_size utterances of the engine's batch (conditioning was laid out per
+            // 16-utterance tile for the engine's batch size at upload)
+            if (e->tc_dirty) {
+                CK(wn_lat_pack(e->tc_image, p, stream));
+                e->tc_dirty = false;
+            }
+            CK(wn_launch_lat(p, e->tc_image, e->B, stream, &e->last));
+        } else if (e->tc_mode) {
             if (batch_size != e->B)
                 return fail(NVWN_EINVAL, "nvwn_run_partial: the tensor-core path needs batch_size equal to the engine's batch size");
             if (e->tc_dirty) {

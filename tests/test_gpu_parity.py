@@ -159,30 +159,52 @@ def _logit_check(za_o, za_g, rel=1e-2, mean_rel=None):
         assert (err / scale).mean() <= mean_rel, f"mean err / scale {(err / scale).mean()}"
 
 
-@pytest.mark.parametrize("kernel", ["stream", "auto", "tc_tile64", "tc_tile64_unfused", "tc_nodup"])
+FP16_KERNELS = ["stream", "lat", "tc", "tc_tile64", "tc_tile64_unfused", "tc_nodup"]
+
+
+def _select_fp16_kernel(kernel, monkeypatch):
+    """Environment switches read once by nvwn_create: which fp16 kernel, and which tile shape / schedule of the tensor-core one."""
+    for k in ("NVWN_FP16_KERNEL", "NVWN_TC_TILE", "NVWN_TC_NODUP", "NVWN_TC_FUSED"):
+        monkeypatch.delenv(k, raising=False)
+    if kernel == "stream":
+        monkeypatch.setenv("NVWN_FP16_KERNEL", "stream")
+    elif kernel == "lat":                          # latency-mode kernel (mma.sync, 16-utterance tiles): what AUTO picks up to 2368 utterances
+        monkeypatch.setenv("NVWN_FP16_KERNEL", "lat")
+    else:                                          # tensor-core (tcgen05) kernel: 32-utterance tiles unless told otherwise
+        monkeypatch.setenv("NVWN_FP16_KERNEL", "tc")
+        if kernel == "tc_nodup":                   # 128-utterance tiles, two threads per utterance (the large-batch variant)
+            monkeypatch.setenv("NVWN_TC_NODUP", "1")
+        if kernel.startswith("tc_tile64"):         # 64-utterance tiles, four threads per utterance
+            monkeypatch.setenv("NVWN_TC_TILE", "64")
+        if kernel == "tc_tile64_unfused":          # the two-round-trip schedule that launches filling the GPU use
+            monkeypatch.setenv("NVWN_TC_FUSED", "0")
+
+
+def _check_sampled_index(p, sel, y):
+    """y must be the first class whose cumulative probability exceeds the selector (reference.cpp:106-121), judged on the
+    kernel's own dumped p; a selector within 1e-4 of a boundary may fall on either side."""
+    cs = np.cumsum(p.astype(np.float64), axis=1)
+    cs /= cs[:, -1:]
+    for b in range(p.shape[0]):
+        lo = int(np.searchsorted(cs[b], sel[b] - 1e-4, side="right"))
+        hi = int(np.searchsorted(cs[b], sel[b] + 1e-4, side="right"))
+        assert lo <= y[b] <= min(hi, p.shape[1] - 1), f"utterance {b}: sampled {y[b]}, expected [{lo}, {hi}] for selector {sel[b]}"
+
+
+@pytest.mark.parametrize("kernel", FP16_KERNELS)
 @pytest.mark.parametrize("shape", [
     (64, 256, 256, 20, 8, 24, 8),
     (64, 128, 256, 20, 4, 16, 4),
     (64, 256, 256, 20, 64, 12, 4),
-    (64, 256, 256, 20, 130, 6, 2),        # two batch tiles, the second one nearly empty
+    (64, 256, 256, 20, 130, 6, 2),        # several batch tiles, the last one nearly empty
     (64, 256, 256, 5, 100, 10, 16),       # odd layer count, partially filled tile
 ])
 def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
     R, S, A, L, B, N, md = shape
-    if kernel == "stream":
-        if B > 64:
-            pytest.skip("covered by the smaller shapes")
-        monkeypatch.setenv("NVWN_FP16_KERNEL", "stream")
-    if kernel == "tc_nodup":                       # 128-utterance tiles, two threads per utterance (the large-batch variant)
-        monkeypatch.setenv("NVWN_TC_NODUP", "1")
-    if kernel.startswith("tc_tile64"):             # 64-utterance tiles, four threads per utterance ("auto" picks 32-utterance
-        monkeypatch.setenv("NVWN_TC_TILE", "64")   # tiles, eight threads per utterance, at these batch sizes)
-    if kernel == "tc_tile64_unfused":              # the two-round-trip schedule that launches filling the GPU use
-        if B > 100:
-            pytest.skip("covered by the smaller shapes")
-        monkeypatch.setenv("NVWN_TC_FUSED", "0")
+    if kernel in ("stream", "tc_tile64_unfused") and B > 64:
+        pytest.skip("covered by the smaller shapes")
+    _select_fp16_kernel(kernel, monkeypatch)
     w = refgen.lively_inputs(21 + B, R, S, A, L, B, N)
-    # moderate the scales a little so that fp16 GEMM inputs stay well inside range
     o32 = cpu_oracle(w, L, B, N, R, S, A, md)
     forced = o32.run(N, B)                                     # the fp32 model's own trajectory as history
     for n_run in (1, N):                                       # step 0 (identical history) and the last step
@@ -192,6 +214,7 @@ def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
         e.set_forced(f)
         y = np.zeros((B, n_run), np.int32)
         e.run(n_run, B, y, dump_activations=True); e.synchronize()
+        assert e.launch_info()["kernel"] == {"stream": 16, "lat": 18}.get(kernel, 17)
         o16 = cpu_oracle(wn_, L, B, n_run, R, S, A, md, prec=po.PREC_FP16); o16.set_forced(f); o16.run(n_run, B)
         o = cpu_oracle(wn_, L, B, n_run, R, S, A, md); o.set_forced(f); o.run(n_run, B)
         ag = e.activations()
@@ -199,6 +222,73 @@ def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
         _logit_check(o.get_za(), ag["za"], 1e-2)                    # vs the fp32 oracle: the north-star tolerance
         assert np.allclose(ag["p"].sum(axis=1), 1.0, atol=1e-3)
         assert np.abs(ag["p"] - o.get_p()).max() <= 1e-2 * o.get_p().max()
+        _check_sampled_index(ag["p"], wn_["selectors"][n_run - 1], y[:, n_run - 1])
+        if kernel != "stream":
+            # intermediate activations of the last step against the fp16-contract oracle
+            ao = o16.activations()
+            for k, tol in (("xt", 2e-2), ("skip", 2e-2), ("zs", 2e-2)):
+                sc = np.abs(ao[k]).max()
+                assert np.abs(ag[k] - ao[k]).max() <= tol * sc, f"{k}: {np.abs(ag[k] - ao[k]).max() / sc}"
+
+
+def _run_range(e, init, count, N, B, y=None):
+    """run_partial over samples [init, init+count) of an N-sample batch (the reference's run_partial + samples_per_chunk)."""
+    e._samples_per_chunk = count
+    e.run_partial(init, N, B, y)
+    e._samples_per_chunk = 0
+
+
+@pytest.mark.parametrize("kernel", ["lat", "tc", "tc_tile64", "tc_tile64_unfused", "tc_nodup"])
+def test_fp16_soak_determinism_and_chunking(kernel, monkeypatch):
+    """The fp16 kernels at the C3 shape (L20 R64 S256 A256, maxDil 512, 64 utterances) over 2000 samples -- several turns of the
+    513-slot history ring and of the dilation cycle: run twice -> identical yOut; run_chunks(97) and three unequal
+    run_partial pieces == one launch, bit for bit (reference: nv_wavenet_test.cu:254,302-304 chunks of 7+1, exact indices)."""
+    R, S, A, L, B, N, md = 64, 256, 256, 20, 64, 2000, 512
+    _select_fp16_kernel(kernel, monkeypatch)
+    w = refgen.lively_inputs(31, R, S, A, L, B, N)
+    e = gpu_engine(w, L, B, N, R, S, A, md, dtype=nw.FP16)
+    y1 = np.zeros((B, N), np.int32); e.run(N, B, y1); e.synchronize()
+    assert len(np.unique(y1)) > 32
+    e.reset_history(); y2 = np.zeros((B, N), np.int32); e.run(N, B, y2); e.synchronize()
+    assert np.array_equal(y1, y2), "run-to-run determinism"
+    e.reset_history(); y3 = np.zeros((B, N), np.int32)
+    seen = []
+    e.run_chunks(97, lambda yo, init, n: seen.append((init, n)), N, B, y3); e.synchronize()
+    assert seen[0] == (0, 97) and seen[-1] == (1940, 60)
+    assert np.array_equal(y1, y3), "run_chunks(97) != one launch"
+    e.reset_history(); y4 = np.zeros((B, N), np.int32)
+    _run_range(e, 0, 1, N, B); _run_range(e, 1, 700, N, B); _run_range(e, 701, 1299, N, B, y4); e.synchronize()
+    assert np.array_equal(y1, y4), "three unequal run_partial pieces != one launch"
+
+
+@pytest.mark.parametrize("kernel", ["lat", "tc", "tc_tile64_unfused"])
+def test_fp16_logits_after_ring_wrap(kernel, monkeypatch):
+    """Teacher-forced logits at step N-1 = 599 > maxDil + 1 = 513 (real ring wrap, every dilation live) against the oracle."""
+    R, S, A, L, B, N, md = 64, 256, 256, 20, 16, 600, 512
+    _select_fp16_kernel(kernel, monkeypatch)
+    w = refgen.lively_inputs(57, R, S, A, L, B, N)
+    forced = np.random.default_rng(5).integers(0, A, (B, N)).astype(np.int32)
+    e = gpu_engine(w, L, B, N, R, S, A, md, dtype=nw.FP16)
+    e.set_forced(forced)
+    y = np.zeros((B, N), np.int32)
+    e.run(N, B, y, dump_activations=True); e.synchronize()
+    o = cpu_oracle(w, L, B, N, R, S, A, md); o.set_forced(forced); o.run(N, B)
+    ag = e.activations()
+    _logit_check(o.get_za(), ag["za"], 1e-2)
+    _check_sampled_index(ag["p"], w["selectors"][N - 1], y[:, N - 1])
+
+
+def test_fp16_latency_kernel_smaller_batch_than_engine():
+    """run(batch_size < engine batch): the first batch_size utterances of the engine's batch (16-utterance tiles are independent)."""
+    R, S, A, L, B, N, md = 64, 256, 256, 6, 40, 30, 8
+    w = refgen.lively_inputs(8, R, S, A, L, B, N)
+    e = gpu_engine(w, L, B, N, R, S, A, md, dtype=nw.FP16, impl=nw.KERNEL_LATENCY)
+    y_all = np.zeros((B, N), np.int32); e.run(N, B, y_all); e.synchronize()
+    e.reset_history()
+    # selectors are indexed with the run's batch size as the stride (nv_wavenet.cuh:144): [N][20] at the front of the buffer
+    e.set_selectors(np.concatenate([np.ascontiguousarray(w["selectors"][:, :20]).reshape(-1), np.zeros(N * (B - 20), np.float32)]))
+    y20 = np.zeros((20, N), np.int32); e.run(N, 20, y20); e.synchronize()
+    assert np.array_equal(y20, y_all[:20])
 
 
 def test_wavenet_infer_c_abi_drop_in():

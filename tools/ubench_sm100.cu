@@ -277,7 +277,7 @@ int main()
         const size_t span = 4u << 20;
         unsigned char* d_src; CK(cudaMalloc(&d_src, span)); CK(cudaMemset(d_src, 1, span));
         CK(cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        for (int ctas : {1, 4, 32, 148}) for (int chunk : {4096, 16384}) for (int nst : {4, 8}) {
+        for (int ctas : {1, 4, 148}) for (int chunk : {4096, 16384, 32768, 65536}) for (int nst : {2, 3}) {
             const int nch = (int)((16u << 20) / chunk);
             k_stream_tma<<<ctas, 64, (size_t)nst * chunk + 256>>>(d_src, span, chunk, nst, nch, d_out); fetch();
             long long mx = 0; for (int i = 0; i < ctas; i++) if (h[i] > mx) mx = h[i];
