@@ -15,8 +15,9 @@
 //                   per sample: relu(skip) -> Zs -> Za -> softmax + categorical sample (warp-local, two utterances per warp)
 //                               -> embedding gather from the shared-memory resident table.
 //   producer warp   streams the weight image (pre-arranged in mma B-fragment order, so that every weight load of a warp is one
-//                   conflict-free 512-byte LDS.128) from L2 through a 2-stage shared-memory ring with bulk TMA + mbarriers,
-//                   one stage per layer, the four matrices of a layer on four barriers.
+//                   conflict-free 512-byte LDS.128) from L2 through a shared-memory ring with bulk TMA + mbarriers: two pieces
+//                   per layer ([Wcur_l | Wprev_l+1] 32 KB, [Wres_l | Wskip_l] 40 KB), two slots per piece type, every slot
+//                   refilled as soon as its occupant is consumed -- each piece is in flight two layers before its use.
 //   Lh (the only HBM stream), biases and the dilated history x[t-d] are prefetched into registers one / two layers ahead.
 //
 // Replaces nv_wavenet_{singleblock,dualblock,persistent}.cuh + matrix_math.cuh + softmax.cuh of the reference for
@@ -44,20 +45,28 @@ constexpr int MAXL = 64;
 
 template <int S>
 struct Cfg {
-    static constexpr int W_PREV = 0, W_CUR = 16384, W_RES = 32768, W_SKIP = 40960;
-    static constexpr int LAYER_BYTES = W_SKIP + S * 128;            // = one ring stage
-    static constexpr int OJP = S == 256 ? 4 : 2;                     // k-step pairs per output-GEMM stage load
-    static constexpr int OLOAD = 32 * OJP * 512;                     // bytes per output-GEMM stage load (all 32 n-tiles)
-    static constexpr int NQ_ZS = (S / 32) / OJP, NQ_ZA = (A / 32) / OJP;
+    // one layer block of the weight image = two ring pieces, in consumption order:
+    //   P1 = [ Wcur_l | Wprev_{(l+1) mod L} ]  (32 KB)      P2 = [ Wres_l | Wskip_l ]  (8 KB + S x 128 B)
+    static constexpr int W_CUR = 0, W_PREV = 16384, W_RES = 32768, W_SKIP = 40960;
+    static constexpr int P1_BYTES = 32768, P2_BYTES = 8192 + S * 128;
+    static constexpr int LAYER_BYTES = P1_BYTES + P2_BYTES;
+    // output GEMMs: 4 + 4 ring pieces per sample, each all 32 n-tiles x OJP k-step pairs
+    static constexpr int NQ_ZS = 4, NQ_ZA = 4;
+    static constexpr int OJP_ZS = S / 128, OJP_ZA = A / 128;         // k-step pairs per piece
+    static constexpr int ZS_PIECE = 32 * OJP_ZS * 512, ZA_PIECE = 32 * OJP_ZA * 512;
+    static constexpr int OPIECE = ZA_PIECE > ZS_PIECE ? ZA_PIECE : ZS_PIECE;
     static constexpr int NSK = S / 64;                               // skip n-tiles per warp
+    // ring: two slots per piece type; output pieces alternate between the two types
+    static constexpr int SLOT1 = P1_BYTES, SLOT2 = P2_BYTES > OPIECE ? P2_BYTES : OPIECE;
     // shared memory map
-    static constexpr uint32_t O_RING = 0;
-    static constexpr uint32_t O_EMB = 2 * LAYER_BYTES;
+    static constexpr uint32_t O_RING1 = 0;                           // 2 x SLOT1
+    static constexpr uint32_t O_RING2 = 2 * SLOT1;                   // 2 x SLOT2
+    static constexpr uint32_t O_EMB = O_RING2 + 2 * SLOT2;
     static constexpr uint32_t O_BOUT = O_EMB + A * EROW * 4;         // fp32: Bskip total [S], Bzs [A], Bza [A]
     static constexpr uint32_t O_XBUF = O_BOUT + (S + 2 * A) * 4;
     static constexpr uint32_t O_HBUF = O_XBUF + 2048;
     static constexpr uint32_t O_EPBUF = O_HBUF + 2048;
-    static constexpr uint32_t O_OB0 = O_EPBUF + 2048;
+    static constexpr uint32_t O_OB0 = O_EPBUF + 2 * TU * EROW * 4;          // two [16 rows][33 words] buffers (sample parity)
     static constexpr uint32_t O_OB1 = O_OB0 + (S / 16) * 512;
     static constexpr uint32_t O_LBUF = O_OB1 + (A / 16) * 512;
     static constexpr uint32_t O_DIL = O_LBUF + TU * LROW * 4;
@@ -136,6 +145,10 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b)
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 __device__ __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // mbarrier by shared-memory address
 __device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -222,26 +235,32 @@ __global__ void lat_pack_kernel(WnParams p, unsigned char* __restrict__ img, Lat
     for (size_t i = g0; i < (size_t)L * 128 * 64; i += gstride) {
         const int l = (int)(i / (128 * 64)), c = (int)(i % (128 * 64)) / 64, k = (int)(i % 64);
         const size_t lb = (size_t)l * im.layer_bytes;
-        put(lb, c, k, 2, Wprev[(size_t)l * 128 * 64 + c + (size_t)k * 128]);
-        put(lb + 16384, c, k, 2, Wcur[(size_t)l * 128 * 64 + c + (size_t)k * 128]);
+        put(lb, c, k, 2, Wcur[(size_t)l * 128 * 64 + c + (size_t)k * 128]);
+        put((size_t)((l + L - 1) % L) * im.layer_bytes + 16384, c, k, 2, Wprev[(size_t)l * 128 * 64 + c + (size_t)k * 128]);   // rides with the layer before it
         if (c < 64) put(lb + 32768, c, k, 2, Wres[(size_t)l * 64 * 64 + c + (size_t)k * 64]);
     }
     for (size_t i = g0; i < (size_t)L * S * 64; i += gstride) {
         const int l = (int)(i / ((size_t)S * 64)), s = (int)((i / 64) % S), k = (int)(i % 64);
         put((size_t)l * im.layer_bytes + 40960, s, k, 2, Wskip[(size_t)l * S * 64 + s + (size_t)k * S]);
     }
-    // output matrices: stage load q holds k-step pairs [q OJP, (q+1) OJP) of all 32 n-tiles
-    const int ojp = S == 256 ? 4 : 2;
-    const size_t oload = (size_t)32 * ojp * 512;
-    for (size_t i = g0; i < (size_t)A * S; i += gstride) {
-        const int a = (int)(i / S), s = (int)(i % S);
-        const int jp = s >> 5, q = jp / ojp;
-        put(im.off_zs + (size_t)q * oload, a, (s & 31) + 32 * (jp % ojp), ojp, Wzs[a + (size_t)s * A]);
+    // output matrices: ring piece q holds k-step pairs [q OJP, (q+1) OJP) of all 32 n-tiles
+    {
+        const int ojp = S / 128;
+        const size_t piece = (size_t)32 * ojp * 512;
+        for (size_t i = g0; i < (size_t)A * S; i += gstride) {
+            const int a = (int)(i / S), s = (int)(i % S);
+            const int jp = s >> 5, q = jp / ojp;
+            put(im.off_zs + (size_t)q * piece, a, (s & 31) + 32 * (jp % ojp), ojp, Wzs[a + (size_t)s * A]);
+        }
     }
-    for (size_t i = g0; i < (size_t)A * A; i += gstride) {
-        const int a = (int)(i / A), z = (int)(i % A);
-        const int jp = z >> 5, q = jp / ojp;
-        put(im.off_za + (size_t)q * oload, a, (z & 31) + 32 * (jp % ojp), ojp, Wza[a + (size_t)z * A]);
+    {
+        const int ojp = A / 128;
+        const size_t piece = (size_t)32 * ojp * 512;
+        for (size_t i = g0; i < (size_t)A * A; i += gstride) {
+            const int a = (int)(i / A), z = (int)(i % A);
+            const int jp = z >> 5, q = jp / ojp;
+            put(im.off_za + (size_t)q * piece, a, (z & 31) + 32 * (jp % ojp), ojp, Wza[a + (size_t)z * A]);
+        }
     }
     float* bias = reinterpret_cast<float*>(img + im.off_bias);
     const __half* Bh = static_cast<const __half*>(p.Bh);
@@ -267,7 +286,11 @@ __global__ void lat_pack_kernel(WnParams p, unsigned char* __restrict__ img, Lat
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int S>
+struct StepIt { int t, l, slot; };       // coordinates of a layer step: sample, layer, history-ring slot of that sample
+
+// DUMP: write the last-sample activations (the host runs the final sample of a dumping launch with this variant).
+// TRC:  record the clock64 timeline (debug; tools/lat_trace.py).
+template <int S, bool DUMP, bool TRC>
 __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const unsigned char* __restrict__ img, const int ntiles_alloc)
 {
     using C = Cfg<S>;
@@ -281,27 +304,28 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
     const int t_begin = p.init_sample, t_end = p.init_sample + p.count;
     const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
 
-    const uint32_t s_full = sm + C::O_BAR;            // [2 stages][4]
-    const uint32_t s_empty = s_full + 8 * 8;          // [2]
+    // mbarriers of the weight ring: piece n lives in slot (n >> 1) & 1 of slot type n & 1; one full / empty pair per slot
+    const uint32_t s_full = sm + C::O_BAR, s_empty = s_full + 32;
     int* dil = reinterpret_cast<int*>(smem_raw + C::O_DIL);
     int* ys = reinterpret_cast<int*>(smem_raw + C::O_YS);      // [TU] current index, [TU] previous index
     float* s_bout = reinterpret_cast<float*>(smem_raw + C::O_BOUT);
+    constexpr int NQ = C::NQ_ZS + C::NQ_ZA;
+    static_assert(NQ == 8, "the ring bookkeeping assumes 8 output pieces per sample");
 
     // debug timeline: role 0 = compute thread 0, role 2 = producer; words (tag << 48 | clock)
-    unsigned long long* trc = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+    unsigned long long* trc = (TRC && p.trace && blockIdx.x == 0) ? p.trace : nullptr;
     int trn = 0;
     const int tr_t = p.trace_t & 0xFFFF;
-#define TRACE(role, tag) do { if (trc && t == tr_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
+#define TRACE(role, tag) do { if (TRC && trc && t == tr_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
 
     if (tid == 0) {
-        for (int i = 0; i < 8; i++) mbar_init_a(s_full + 8 * i, 1);
-        mbar_init_a(s_empty, NCW); mbar_init_a(s_empty + 8, NCW);
+        for (int i = 0; i < 4; i++) { mbar_init_a(s_full + 8 * i, 1); mbar_init_a(s_empty + 8 * i, NCW); }
         fence_mbar_init();
         int d = 1;                                     // dilation of layer l (nv_wavenet.cuh:99-111): 1,2,4..maxDil,1,2,...
         for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; }
     }
-    {   // embedding table of the current sample's index -> shared memory (rows padded to 33 words: gathers of different
-        // rows fall into different banks); output-layer biases
+    {   // current-index embedding table -> shared memory (rows padded to 33 words: gathers of different rows fall into
+        // different banks); output-layer biases; feedback state
         const uint32_t* ec = static_cast<const uint32_t*>(p.embCur);
         for (int i = tid; i < A * 32; i += NT) sts32(sm + C::O_EMB + ((i >> 5) * EROW + (i & 31)) * 4, ec[i]);
         for (int i = tid; i < S; i += NT) s_bout[i] = gbias[im.b_skpre + (size_t)(L - 1) * S + i];
@@ -315,29 +339,28 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
     __syncthreads();
 
     if (warp == NCW) {
-        // =============================================================== TMA producer (one lane)
+        // =============================================================== TMA producer (one lane): the pieces in consumption order,
+        // each refilled as soon as ITS previous occupant has been consumed (two layers of lead for every piece)
         if (lane == 0) {
-            uint32_t cnt = 0;
+            uint32_t pc = 0;
+            auto put = [&](const unsigned char* src, uint32_t bytes) {
+                const uint32_t idx = (pc >> 1) & 1, bo = ((pc & 1) * 2 + idx) * 8;
+                const uint32_t dst = (pc & 1) ? sm + C::O_RING2 + idx * C::SLOT2 : sm + C::O_RING1 + idx * C::SLOT1;
+                mbar_wait_a(s_empty + bo, ((pc >> 2) & 1) ^ 1);
+                mbar_expect_a(s_full + bo, bytes);
+                tma_load_a(dst, src, bytes, s_full + bo);
+                pc++;
+            };
             for (int t = t_begin; t < t_end; t++) {
-                for (int l = 0; l < L; l++, cnt++) {
-                    const uint32_t st = cnt & 1, dst = sm + C::O_RING + st * C::LAYER_BYTES, fb = s_full + st * 32;
-                    mbar_wait_a(s_empty + 8 * st, ((cnt >> 1) & 1) ^ 1);
+                for (int l = 0; l < L; l++) {
                     const unsigned char* src = img + (size_t)l * im.layer_bytes;
-                    mbar_expect_a(fb, 16384);          tma_load_a(dst + C::W_PREV, src + C::W_PREV, 16384, fb);
-                    mbar_expect_a(fb + 8, 16384);      tma_load_a(dst + C::W_CUR, src + C::W_CUR, 16384, fb + 8);
-                    mbar_expect_a(fb + 16, 8192);      tma_load_a(dst + C::W_RES, src + C::W_RES, 8192, fb + 16);
-                    mbar_expect_a(fb + 24, S * 128);   tma_load_a(dst + C::W_SKIP, src + C::W_SKIP, S * 128, fb + 24);
+                    put(src, C::P1_BYTES);
+                    put(src + C::P1_BYTES, C::P2_BYTES);
                     TRACE(2, 100 + l);
                 }
-                for (int q = 0; q < C::NQ_ZS + C::NQ_ZA; q++, cnt++) {
-                    const uint32_t st = cnt & 1, dst = sm + C::O_RING + st * C::LAYER_BYTES, fb = s_full + st * 32;
-                    mbar_wait_a(s_empty + 8 * st, ((cnt >> 1) & 1) ^ 1);
-                    const unsigned char* src = q < C::NQ_ZS ? img + im.off_zs + (size_t)q * C::OLOAD : img + im.off_za + (size_t)(q - C::NQ_ZS) * C::OLOAD;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {      // quarter k = n-tiles [8k, 8k+8) = compute warps 2k, 2k+1
-                        mbar_expect_a(fb + 8 * k, C::OLOAD / 4);
-                        tma_load_a(dst + k * (C::OLOAD / 4), src + k * (C::OLOAD / 4), C::OLOAD / 4, fb + 8 * k);
-                    }
+                for (int q = 0; q < NQ; q++) {
+                    put(q < C::NQ_ZS ? img + im.off_zs + (size_t)q * C::ZS_PIECE : img + im.off_za + (size_t)(q - C::NQ_ZS) * C::ZA_PIECE,
+                        q < C::NQ_ZS ? C::ZS_PIECE : C::ZA_PIECE);
                     TRACE(2, 200 + q);
                 }
             }
@@ -347,189 +370,227 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
         const int w = warp, g = lane >> 2, t4 = lane & 3;
         const int b0 = tile * TU + g, b1 = b0 + 8;
         const bool v0 = b0 < B, v1 = b1 < B;
+        const uint32_t cstride = (uint32_t)ntiles_alloc * 4096u, rstride = (uint32_t)ntiles_alloc * 2048u;
         const unsigned char* gcond = static_cast<const unsigned char*>(p.Lh) + (size_t)tile * 4096 + (size_t)(w * 32 + lane) * 16;
         unsigned char* gring = static_cast<unsigned char*>(p.ring) + (size_t)tile * 2048 + (size_t)lane * 16;
         const float* gbl = gbias + im.b_layer + (size_t)(w * 4 + t4) * 8;
-        const uint4 zero4 = make_uint4(0, 0, 0, 0);
-        auto cond_ld = [&](int t, int l) -> uint4 {
-            if (t >= t_end) return zero4;
-            return ldg_nc_v4(gcond + ((size_t)t * L + l) * ntiles_alloc * 4096);
-        };
-        auto ring_ptr = [&](int t, int l) -> unsigned char* { return gring + ((size_t)(t % slots) * L + l) * ntiles_alloc * 2048; };
-        auto prev_ld = [&](uint32_t (&x)[4][4], int t, int l) {
-            const int d = dil[l];
-            if (t >= t_end || t < d) {
+        const int jw = w >> 1, hw = w & 1;             // this warp's 8 channels = k-step jw, half hw of an activation tile
+        const uint32_t lane16 = (uint32_t)lane * 16;
+        const uint32_t xchg = (uint32_t)(jw * 512 + hw * 8) + lane16;
+        const int cw = 8 * w + 2 * t4;                 // first of the thread's two channels inside the warp's slice
+        // this thread's B-fragment offsets inside the ring pieces
+        const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16;   // + 512 for the second k-step pair
+        const uint32_t o_res = (uint32_t)(w * 2) * 512 + lane16, o_skip = 8192u + (uint32_t)(w * C::NSK * 2) * 512 + lane16;
+        const uint32_t o_out = (uint32_t)(4 * w) * 512;                                                         // output pieces: x OJP, + lane16
+
+        auto advance = [&](StepIt& it) { if (++it.l == L) { it.l = 0; it.t++; if (++it.slot == slots) it.slot = 0; } };
+        // dilated history x_l[t - d] of step `it` -> A fragments (zero before the start of the utterance, nv_wavenet.cuh:106)
+        auto ldP = [&](uint32_t (&x)[4][4], const StepIt& it) {
+            const int d = dil[it.l];
+            if (it.t >= t_end || it.t < d) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0; }
                 return;
             }
-            const unsigned char* src = ring_ptr(t - d, l);
+            int sl = it.slot - d; if (sl < 0) sl += slots;
+            const unsigned char* src = gring + (size_t)((uint32_t)(sl * L + it.l) * rstride);
 #pragma unroll
             for (int j = 0; j < 4; j++) { const uint4 v = ldg_cg_v4(src + j * 512); x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w; }
         };
-        const int jw = w >> 1, hw = w & 1;             // this warp's 8 channels = k-step jw, half hw of an activation tile
-        const uint32_t xchg = (uint32_t)(jw * 512 + lane * 16 + hw * 8);
+        const unsigned char* cptr;                     // conditioning of step it3 (steps are consecutive in memory)
+        auto ldC = [&](const StepIt& it) -> uint4 {
+            const unsigned char* src = cptr;
+            cptr += cstride;
+            if (it.t >= t_end) return make_uint4(0, 0, 0, 0);
+            return ldg_nc_v4(src);
+        };
+        auto release = [&](uint32_t bar) { __syncwarp(); if (lane == 0) mbar_arrive_a(bar); };
 
-        uint32_t xa[4][4], xp[4][4], xpn[4][4];
-        float xres[4];
+        uint32_t xa[4][4], pbA[4][4], pbB[4][4];
+        uint4 cbA, cbB;
+        float accp[2][4];                              // pre-activation of the coming step: Wprev.x[t-d] + Bh + Lh
+        float2 brn;                                    // Bres pair of the coming step
+        float4 bh_next; float2 br_next;                // Bh / Bres pairs of the step after (prefetched a layer ahead)
+        float xres[4] = {0.f, 0.f, 0.f, 0.f};
         float sk[C::NSK][4];
 #pragma unroll
         for (int i = 0; i < C::NSK; i++) sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
 
-        // previous-index embedding rows of the first sample -> epbuf (A-fragment order)
-        if (w < 4) {
+        // accp <- (Bh + Lh) + Wprev . x[t-d] for the coming step `it1`, whose history / conditioning sit in (pb, cb) and whose
+        // Wprev rides in the SAME ring piece as the current layer's Wcur (`p1`; the very first one comes from global memory);
+        // then refill (pb, cb) with the step `it3`.  Independent of the current layer's data: fills the h exchange.
+        StepIt it1{0, 0, 0}, it3{0, 0, 0};
+        auto prep = [&](uint32_t (&pb)[4][4], uint4& cb, const uint32_t p1, const bool from_global) {
+            brn = br_next;
+            {
+                const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
+                accp[0][0] = bh_next.x + c0.x; accp[0][1] = bh_next.y + c0.y; accp[0][2] = bh_next.x + c1.x; accp[0][3] = bh_next.y + c1.y;
+                accp[1][0] = bh_next.z + c2.x; accp[1][1] = bh_next.w + c2.y; accp[1][2] = bh_next.z + c3.x; accp[1][3] = bh_next.w + c3.y;
+            }
+            if (it1.t < t_end) {
+                uint4 bt0, bg0, bt1, bg1;
+                if (from_global) {
+                    const unsigned char* gp = img + (size_t)(L - 1) * im.layer_bytes + C::W_PREV;
+                    bt0 = ldg_nc_v4(gp + o_t0); bg0 = ldg_nc_v4(gp + o_g0); bt1 = ldg_nc_v4(gp + o_t0 + 512); bg1 = ldg_nc_v4(gp + o_g0 + 512);
+                } else {
+                    bt0 = lds128(p1 + C::W_PREV + o_t0); bg0 = lds128(p1 + C::W_PREV + o_g0);
+                    bt1 = lds128(p1 + C::W_PREV + o_t0 + 512); bg1 = lds128(p1 + C::W_PREV + o_g0 + 512);
+                }
+                float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};         // second half of K: independent chains
+                hmma(accp[0], pb[0], bt0.x, bt0.y); hmma(accp[1], pb[0], bg0.x, bg0.y); hmma(u0, pb[2], bt1.x, bt1.y); hmma(u1, pb[2], bg1.x, bg1.y);
+                hmma(accp[0], pb[1], bt0.z, bt0.w); hmma(accp[1], pb[1], bg0.z, bg0.w); hmma(u0, pb[3], bt1.z, bt1.w); hmma(u1, pb[3], bg1.z, bg1.w);
+#pragma unroll
+                for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
+            }
+            ldP(pb, it3);
+            cb = ldC(it3);
+            advance(it1); advance(it3);
+            bh_next = *reinterpret_cast<const float4*>(gbl + it1.l * 256);
+            br_next = *reinterpret_cast<const float2*>(gbl + it1.l * 256 + 4);
+        };
+
+        // ---------------- prologue: previous-index rows of the first sample, prefetch pipeline
+        {
             const uint32_t* ep = static_cast<const uint32_t*>(p.embPrev);
-            const int yp0 = ys[TU + g], yp1 = ys[TU + g + 8];
-            uint4 v;
-            v.x = ep[yp0 * 32 + 8 * w + t4]; v.y = ep[yp1 * 32 + 8 * w + t4];
-            v.z = ep[yp0 * 32 + 8 * w + 4 + t4]; v.w = ep[yp1 * 32 + 8 * w + 4 + t4];
-            sts128(sm + C::O_EPBUF + w * 512 + lane * 16, v);
+            sts32(sm + C::O_EPBUF + (g * EROW + 4 * w + t4) * 4, ep[ys[TU + g] * 32 + 4 * w + t4]);
+            sts32(sm + C::O_EPBUF + ((g + 8) * EROW + 4 * w + t4) * 4, ep[ys[TU + g + 8] * 32 + 4 * w + t4]);
         }
-        // prefetch pipeline: conditioning two layers ahead, biases and history one layer ahead
-        uint4 cd0 = cond_ld(t_begin, 0), cd1 = L > 1 ? cond_ld(t_begin, 1) : cond_ld(t_begin + 1, 0), cd2;
-        float4 bs0 = *reinterpret_cast<const float4*>(gbl), bs1;
-        float2 br0 = *reinterpret_cast<const float2*>(gbl + 4), br1;
-        prev_ld(xp, t_begin, 0);
+        StepIt it0{t_begin, 0, t_begin % slots};
+        {
+            it1 = it0; it3 = it0;
+            cptr = gcond + (size_t)t_begin * L * cstride;
+            ldP(pbA, it0); cbA = ldC(it0);                              // step 0: consumed right here
+            StepIt i1 = it0; advance(i1);
+            ldP(pbB, i1); cbB = ldC(i1);                                // step 1 -> buffer B
+            advance(it3); advance(it3);                                 // prep() refills buffer A with step 2 ...
+            bh_next = *reinterpret_cast<const float4*>(gbl); br_next = *reinterpret_cast<const float2*>(gbl + 4);
+            prep(pbA, cbA, 0, true);                                    // ... leaving it1 = step 1, it3 = step 3
+        }
         bar_compute();
 
-        uint32_t cnt = 0;
-        for (int t = t_begin; t < t_end; t++) {
-            const bool last = p.dump && t == t_end - 1;
-            // ---------------- embedding (reference.cpp:42-57): x0 = [tanh](embPrev[yPrev] + embCur[yCur]); every warp builds
-            // the whole A-fragment set redundantly from shared memory -- no exchange, no barrier
-            const int yc0 = ys[g], yc1 = ys[g + 8];
-            const float sel0 = (2 * w + 0 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w] : 0.5f;
-            const float sel1 = (2 * w + 1 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w + 1] : 0.5f;
-            if (tid == 0) TRACE(0, 1);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint4 pv = lds128(sm + C::O_EPBUF + j * 512 + lane * 16);
-                const uint32_t pvv[4] = {pv.x, pv.y, pv.z, pv.w};
-                uint32_t cv[4];
-                cv[0] = lds32(sm + C::O_EMB + (yc0 * EROW + 8 * j + t4) * 4);
-                cv[1] = lds32(sm + C::O_EMB + (yc1 * EROW + 8 * j + t4) * 4);
-                cv[2] = lds32(sm + C::O_EMB + (yc0 * EROW + 8 * j + 4 + t4) * 4);
-                cv[3] = lds32(sm + C::O_EMB + (yc1 * EROW + 8 * j + 4 + t4) * 4);
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const float2 a = unpack_h2(pvv[r]), c = unpack_h2(cv[r]);
-                    float e0 = a.x + c.x, e1 = a.y + c.y;
-                    if (p.tanhEmbed) { e0 = wn::tanhf_fast(e0); e1 = wn::tanhf_fast(e1); }
-                    xa[j][r] = pack_h2(e0, e1);
-                    if (j == jw && r == 2 * hw) { xres[0] = e0; xres[1] = e1; }
-                    if (j == jw && r == 2 * hw + 1) { xres[2] = e0; xres[3] = e1; }
-                }
-            }
-            // history of layer 0, and the previous-index rows of the NEXT sample (= this sample's current index)
-            uint4 epn = zero4;
-            if (w < 4) {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (j == w) stg_v4(ring_ptr(t, 0) + j * 512, make_uint4(xa[j][0], xa[j][1], xa[j][2], xa[j][3]));
-                const uint32_t* ep = static_cast<const uint32_t*>(p.embPrev);
-                epn.x = __ldg(ep + yc0 * 32 + 8 * w + t4); epn.y = __ldg(ep + yc1 * 32 + 8 * w + t4);
-                epn.z = __ldg(ep + yc0 * 32 + 8 * w + 4 + t4); epn.w = __ldg(ep + yc1 * 32 + 8 * w + 4 + t4);
-            }
-            if (tid == 0) TRACE(0, 2);
-            const int lep = L > 2 ? 2 : L - 1;          // layer at which the next sample's previous-index rows are parked
+        // ring bookkeeping: a layer step uses slot `sb` of both piece types; the parity of its barriers is `fph`
+        uint32_t sb = 0, fph = 0;
 
-            for (int l = 0; l < L; l++, cnt++) {
-                const uint32_t st = sm + C::O_RING + (cnt & 1) * C::LAYER_BYTES, fb = s_full + (cnt & 1) * 32, ph = (cnt >> 1) & 1;
-                // ---- prefetches
-                int t1 = t, l1 = l + 1; if (l1 == L) { l1 = 0; t1 = t + 1; }
-                int t2 = t1, l2 = l1 + 1; if (l2 == L) { l2 = 0; t2 = t1 + 1; }
-                prev_ld(xpn, t1, l1);
-                cd2 = cond_ld(t2, l2);
-                bs1 = *reinterpret_cast<const float4*>(gbl + (size_t)l1 * 256);
-                br1 = *reinterpret_cast<const float2*>(gbl + (size_t)l1 * 256 + 4);
-                // ---- a = Wcur.x + Wprev.x[t-d] + (Bh + Lh)   (nv_wavenet.cuh:131-157)
-                float acc[2][4];
-                {
-                    const float2 c0 = unpack_h2(cd0.x), c1 = unpack_h2(cd0.y), c2 = unpack_h2(cd0.z), c3 = unpack_h2(cd0.w);
-                    acc[0][0] = bs0.x + c0.x; acc[0][1] = bs0.y + c0.y; acc[0][2] = bs0.x + c1.x; acc[0][3] = bs0.y + c1.y;
-                    acc[1][0] = bs0.z + c2.x; acc[1][1] = bs0.w + c2.y; acc[1][2] = bs0.z + c3.x; acc[1][3] = bs0.w + c3.y;
-                }
-                mbar_wait_a(fb + 8, ph);
+        // one layer step.  (pb, cb) hold the history / conditioning of the NEXT step.
+        auto step = [&](const int t, const int l, uint32_t (&pb)[4][4], uint4& cb) {
+            const uint32_t p1 = sm + C::O_RING1 + sb * C::SLOT1, p2 = sm + C::O_RING2 + sb * C::SLOT2;
+            const uint32_t f1 = s_full + sb * 8, f2 = s_full + 16 + sb * 8, e1 = s_empty + sb * 8, e2 = s_empty + 16 + sb * 8;
+            const float2 br = brn;
+            // ---- a = Wcur.x + [Wprev.x[t-d] + Bh + Lh]   (nv_wavenet.cuh:131-157); the two halves of K as independent chains
+            mbar_wait_a(f1, fph);
+            {
+                const uint4 bt0 = lds128(p1 + o_t0), bg0 = lds128(p1 + o_g0), bt1 = lds128(p1 + o_t0 + 512), bg1 = lds128(p1 + o_g0 + 512);
+                float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
+                hmma(accp[0], xa[0], bt0.x, bt0.y); hmma(accp[1], xa[0], bg0.x, bg0.y); hmma(u0, xa[2], bt1.x, bt1.y); hmma(u1, xa[2], bg1.x, bg1.y);
+                hmma(accp[0], xa[1], bt0.z, bt0.w); hmma(accp[1], xa[1], bg0.z, bg0.w); hmma(u0, xa[3], bt1.z, bt1.w); hmma(u1, xa[3], bg1.z, bg1.w);
 #pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const uint4 bt = lds128(st + C::W_CUR + (w * 2 + jp) * 512 + lane * 16);
-                    const uint4 bg = lds128(st + C::W_CUR + ((8 + w) * 2 + jp) * 512 + lane * 16);
-                    hmma(acc[0], xa[2 * jp], bt.x, bt.y); hmma(acc[1], xa[2 * jp], bg.x, bg.y);
-                    hmma(acc[0], xa[2 * jp + 1], bt.z, bt.w); hmma(acc[1], xa[2 * jp + 1], bg.z, bg.w);
-                }
-                mbar_wait_a(fb, ph);
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const uint4 bt = lds128(st + C::W_PREV + (w * 2 + jp) * 512 + lane * 16);
-                    const uint4 bg = lds128(st + C::W_PREV + ((8 + w) * 2 + jp) * 512 + lane * 16);
-                    hmma(acc[0], xp[2 * jp], bt.x, bt.y); hmma(acc[1], xp[2 * jp], bg.x, bg.y);
-                    hmma(acc[0], xp[2 * jp + 1], bt.z, bt.w); hmma(acc[1], xp[2 * jp + 1], bg.z, bg.w);
-                }
-                // ---- h = tanh(a[:R]) * sigmoid(a[R:])   (packed fp16 MUFU; sigmoid(x) = 0.5 tanh(x/2) + 0.5)
+                for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
+            }
+            // ---- h = tanh(a[:R]) * sigmoid(a[R:])   (packed fp16 MUFU; sigmoid(x) = 0.5 tanh(x/2) + 0.5)
+            {
                 const __half2 half = __floats2half2_rn(0.5f, 0.5f);
-                const __half2 tg0 = wn::tanh_h2(h2(pack_h2(acc[0][0], acc[0][1]))), tg1 = wn::tanh_h2(h2(pack_h2(acc[0][2], acc[0][3])));
-                const __half2 sg0 = __hfma2(wn::tanh_h2(h2(pack_h2(0.5f * acc[1][0], 0.5f * acc[1][1]))), half, half);
-                const __half2 sg1 = __hfma2(wn::tanh_h2(h2(pack_h2(0.5f * acc[1][2], 0.5f * acc[1][3]))), half, half);
+                const __half2 tg0 = wn::tanh_h2(h2(pack_h2(accp[0][0], accp[0][1]))), tg1 = wn::tanh_h2(h2(pack_h2(accp[0][2], accp[0][3])));
+                const __half2 sg0 = __hfma2(wn::tanh_h2(h2(pack_h2(0.5f * accp[1][0], 0.5f * accp[1][1]))), half, half);
+                const __half2 sg1 = __hfma2(wn::tanh_h2(h2(pack_h2(0.5f * accp[1][2], 0.5f * accp[1][3]))), half, half);
                 sts64(sm + C::O_HBUF + xchg, u32(__hmul2(tg0, sg0)), u32(__hmul2(tg1, sg1)));
-                bar_compute();
-                if (l == lep && w < 4) sts128(sm + C::O_EPBUF + w * 512 + lane * 16, epn);   // every warp has read the old rows long ago
-                uint32_t ha[4][4];
+            }
+            if (tid == 0) TRACE(0, 12);
+            // ---- while the other warps finish their part of h: the dilated-history half of the next step's pre-activation
+            // (after the last layer: layer 0 of the next sample); then this piece of the ring is free
+            prep(pb, cb, p1, false);
+            release(e1);
+            bar_compute();
+            uint32_t ha[4][4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) load_a(ha[j], sm + C::O_HBUF + j * 512 + lane * 16);
-                if (tid == 0) TRACE(0, 10);
-                // ---- x' = Wres.h + Bres + x   (nv_wavenet.cuh:185-207)
-                float ra[4] = {br0.x + xres[0], br0.y + xres[1], br0.x + xres[2], br0.y + xres[3]};
-                mbar_wait_a(fb + 16, ph);
+            for (int j = 0; j < 4; j++) load_a(ha[j], sm + C::O_HBUF + j * 512 + lane16);
+            if (tid == 0) TRACE(0, 10);
+            // ---- x' = Wres.h + Bres + x   (nv_wavenet.cuh:185-207); two half-K chains
+            float ra[4] = {0.f, 0.f, 0.f, 0.f}, rb[4] = {0.f, 0.f, 0.f, 0.f};
+            mbar_wait_a(f2, fph);
+            {
+                const uint4 bw0 = lds128(p2 + o_res), bw1 = lds128(p2 + o_res + 512);
+                hmma(ra, ha[0], bw0.x, bw0.y); hmma(rb, ha[2], bw1.x, bw1.y);
+                hmma(ra, ha[1], bw0.z, bw0.w); hmma(rb, ha[3], bw1.z, bw1.w);
+            }
+            xres[0] = ((ra[0] + rb[0]) + br.x) + xres[0]; xres[1] = ((ra[1] + rb[1]) + br.y) + xres[1];
+            xres[2] = ((ra[2] + rb[2]) + br.x) + xres[2]; xres[3] = ((ra[3] + rb[3]) + br.y) + xres[3];
+            if (l + 1 < L) {
+                const uint32_t x01 = pack_h2(xres[0], xres[1]), x23 = pack_h2(xres[2], xres[3]);
+                sts64(sm + C::O_XBUF + xchg, x01, x23);
+                stg_v2(gring + (size_t)((uint32_t)(it0.slot * L + l + 1) * rstride) + jw * 512 + hw * 8, x01, x23);
+            }
+            if (tid == 0) TRACE(0, 14);
+            if (DUMP) {
+                if (v0) { p.xtOut[((size_t)l * B + b0) * R + cw] = xres[0]; p.xtOut[((size_t)l * B + b0) * R + cw + 1] = xres[1]; }
+                if (v1) { p.xtOut[((size_t)l * B + b1) * R + cw] = xres[2]; p.xtOut[((size_t)l * B + b1) * R + cw + 1] = xres[3]; }
+            }
+            // ---- while the other warps finish their part of x': skip += Wskip.h   (biases are added once, after the last layer)
 #pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const uint4 bw = lds128(st + C::W_RES + (w * 2 + jp) * 512 + lane * 16);
-                    hmma(ra, ha[2 * jp], bw.x, bw.y);
-                    hmma(ra, ha[2 * jp + 1], bw.z, bw.w);
-                }
-                xres[0] = ra[0]; xres[1] = ra[1]; xres[2] = ra[2]; xres[3] = ra[3];
-                if (l + 1 < L) {
-                    const uint32_t x01 = pack_h2(ra[0], ra[1]), x23 = pack_h2(ra[2], ra[3]);
-                    sts64(sm + C::O_XBUF + xchg, x01, x23);
-                    stg_v2(ring_ptr(t, l + 1) + jw * 512 + hw * 8, x01, x23);
-                }
-                if (last) {
-                    const int c = 8 * w + 2 * t4;
-                    if (v0) { p.xtOut[((size_t)l * B + b0) * R + c] = ra[0]; p.xtOut[((size_t)l * B + b0) * R + c + 1] = ra[1]; }
-                    if (v1) { p.xtOut[((size_t)l * B + b1) * R + c] = ra[2]; p.xtOut[((size_t)l * B + b1) * R + c + 1] = ra[3]; }
-                }
-                // ---- skip += Wskip.h   (biases are added once, after the last layer)
-                mbar_wait_a(fb + 24, ph);
+            for (int jp = 0; jp < 2; jp++) {
+                uint4 bw[C::NSK];
+#pragma unroll
+                for (int i = 0; i < C::NSK; i++) bw[i] = lds128(p2 + o_skip + (i * 2 + jp) * 512);
+#pragma unroll
+                for (int i = 0; i < C::NSK; i++) hmma(sk[i], ha[2 * jp], bw[i].x, bw[i].y);
+#pragma unroll
+                for (int i = 0; i < C::NSK; i++) hmma(sk[i], ha[2 * jp + 1], bw[i].z, bw[i].w);
+            }
+            release(e2);
+            if (tid == 0) TRACE(0, 15);
+            if (DUMP) {
+                const float* pre = gbias + im.b_skpre + (size_t)l * S;
 #pragma unroll
                 for (int i = 0; i < C::NSK; i++) {
-#pragma unroll
-                    for (int jp = 0; jp < 2; jp++) {
-                        const uint4 bw = lds128(st + C::W_SKIP + ((w * C::NSK + i) * 2 + jp) * 512 + lane * 16);
-                        hmma(sk[i], ha[2 * jp], bw.x, bw.y);
-                        hmma(sk[i], ha[2 * jp + 1], bw.z, bw.w);
-                    }
+                    const int c = 8 * (w * C::NSK + i) + 2 * t4;
+                    float o0 = sk[i][0] + pre[c], o1 = sk[i][1] + pre[c + 1], o2 = sk[i][2] + pre[c], o3 = sk[i][3] + pre[c + 1];
+                    if (l == L - 1) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
+                    if (v0) { p.skipOut[((size_t)l * B + b0) * S + c] = o0; p.skipOut[((size_t)l * B + b0) * S + c + 1] = o1; }
+                    if (v1) { p.skipOut[((size_t)l * B + b1) * S + c] = o2; p.skipOut[((size_t)l * B + b1) * S + c + 1] = o3; }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_a(s_empty + 8 * (cnt & 1));
-                if (last) {
-                    const float* pre = gbias + im.b_skpre + (size_t)l * S;
+            }
+            if (l + 1 < L) {
+                bar_compute();
 #pragma unroll
-                    for (int i = 0; i < C::NSK; i++) {
-                        const int c = 8 * (w * C::NSK + i) + 2 * t4;
-                        float o0 = sk[i][0] + pre[c], o1 = sk[i][1] + pre[c + 1], o2 = sk[i][2] + pre[c], o3 = sk[i][3] + pre[c + 1];
-                        if (l == L - 1) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
-                        if (v0) { p.skipOut[((size_t)l * B + b0) * S + c] = o0; p.skipOut[((size_t)l * B + b0) * S + c + 1] = o1; }
-                        if (v1) { p.skipOut[((size_t)l * B + b1) * S + c] = o2; p.skipOut[((size_t)l * B + b1) * S + c + 1] = o3; }
-                    }
+                for (int j = 0; j < 4; j++) load_a(xa[j], sm + C::O_XBUF + j * 512 + lane16);
+            }
+            if (tid == 0) TRACE(0, 11);
+            fph ^= sb; sb ^= 1;                        // slot alternates every step, barrier parity every second step
+        };
+
+        uint32_t kp = 0, epar = 0;                     // parity of the global step count / of the sample (epbuf buffer)
+        for (int t = t_begin; t < t_end; t++) {
+            // ---------------- embedding (reference.cpp:42-57): x0 = [tanh](embPrev[yPrev] + embCur[yCur]), this warp's 8 channels
+            if (tid == 0) TRACE(0, 1);
+            const float sel0 = (2 * w + 0 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w] : 0.5f;
+            const float sel1 = (2 * w + 1 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w + 1] : 0.5f;
+            {
+                const int yc0 = ys[g], yc1 = ys[g + 8];
+                const uint32_t eo = sm + C::O_EPBUF + epar * (TU * EROW * 4);
+                const float2 a0 = unpack_h2(lds32(eo + (g * EROW + 4 * w + t4) * 4)), a1 = unpack_h2(lds32(eo + ((g + 8) * EROW + 4 * w + t4) * 4));
+                const float2 c0 = unpack_h2(lds32(sm + C::O_EMB + (yc0 * EROW + 4 * w + t4) * 4)), c1 = unpack_h2(lds32(sm + C::O_EMB + (yc1 * EROW + 4 * w + t4) * 4));
+                xres[0] = a0.x + c0.x; xres[1] = a0.y + c0.y; xres[2] = a1.x + c1.x; xres[3] = a1.y + c1.y;
+                if (p.tanhEmbed) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) xres[i] = wn::tanhf_fast(xres[i]);
                 }
-                if (l + 1 < L) {
-                    bar_compute();
+                const uint32_t x01 = pack_h2(xres[0], xres[1]), x23 = pack_h2(xres[2], xres[3]);
+                sts64(sm + C::O_XBUF + xchg, x01, x23);
+                stg_v2(gring + (size_t)((uint32_t)(it0.slot * L) * rstride) + jw * 512 + hw * 8, x01, x23);
+                // previous-index rows of the NEXT sample (= this sample's current index): global -> shared, asynchronously
+                const unsigned char* ep = static_cast<const unsigned char*>(p.embPrev);
+                const uint32_t en = sm + C::O_EPBUF + (epar ^ 1) * (TU * EROW * 4);
+                cp_async4(en + (g * EROW + 4 * w + t4) * 4, ep + (size_t)yc0 * 128 + (4 * w + t4) * 4);
+                cp_async4(en + ((g + 8) * EROW + 4 * w + t4) * 4, ep + (size_t)yc1 * 128 + (4 * w + t4) * 4);
+                cp_async_commit();
+            }
+            bar_compute();
 #pragma unroll
-                    for (int j = 0; j < 4; j++) load_a(xa[j], sm + C::O_XBUF + j * 512 + lane * 16);
-                }
-                if (tid == 0) TRACE(0, 11);
-#pragma unroll
-                for (int j = 0; j < 4; j++) { xp[j][0] = xpn[j][0]; xp[j][1] = xpn[j][1]; xp[j][2] = xpn[j][2]; xp[j][3] = xpn[j][3]; }
-                cd0 = cd1; cd1 = cd2; bs0 = bs1; br0 = br1;
+            for (int j = 0; j < 4; j++) load_a(xa[j], sm + C::O_XBUF + j * 512 + lane16);
+            if (tid == 0) TRACE(0, 2);
+
+            for (int l = 0; l < L; l++) {
+                if (kp == 0) step(t, l, pbB, cbB); else step(t, l, pbA, cbA);
+                kp ^= 1;
             }
 
             // ---------------- relu(skip + bias) -> Zs -> Za   (reference.cpp:93-104)
@@ -537,7 +598,7 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
             for (int i = 0; i < C::NSK; i++) {
                 const int nt = w * C::NSK + i, c = 8 * nt + 2 * t4;
                 const float b0f = s_bout[c], b1f = s_bout[c + 1];
-                sts64(sm + C::O_OB0 + (nt >> 1) * 512 + lane * 16 + (nt & 1) * 8,
+                sts64(sm + C::O_OB0 + (nt >> 1) * 512 + lane16 + (nt & 1) * 8,
                       pack_h2(fmaxf(sk[i][0] + b0f, 0.f), fmaxf(sk[i][1] + b1f, 0.f)), pack_h2(fmaxf(sk[i][2] + b0f, 0.f), fmaxf(sk[i][3] + b1f, 0.f)));
                 sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
             }
@@ -549,30 +610,33 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
                 const int c = 32 * w + 8 * i + 2 * t4;
                 zz[i][0] = zz[i][2] = s_bout[S + c]; zz[i][1] = zz[i][3] = s_bout[S + c + 1];
             }
-            for (int q = 0; q < C::NQ_ZS; q++, cnt++) {
-                const uint32_t st = sm + C::O_RING + (cnt & 1) * C::LAYER_BYTES, fb = s_full + (cnt & 1) * 32, ph = (cnt >> 1) & 1;
-                mbar_wait_a(fb + 8 * (w >> 1), ph);
-#pragma unroll
-                for (int jp = 0; jp < C::OJP; jp++) {
+            // the 8 output pieces continue the ring sequence: piece q sits in slot type q & 1, slot sb ^ (q >> 1 & 1)
+            auto out_gemm = [&](const int q, const int ojp, const uint32_t abuf, const int kp0) {
+                const uint32_t idx = sb ^ ((q >> 1) & 1), bo = ((q & 1) * 2 + idx) * 8;
+                const uint32_t st = ((q & 1) ? sm + C::O_RING2 + idx * C::SLOT2 : sm + C::O_RING1 + idx * C::SLOT1) + o_out * ojp + lane16;
+                mbar_wait_a(s_full + bo, fph ^ (((sb + (q >> 1)) >> 1) & 1));
+                for (int jp = 0; jp < ojp; jp++) {
                     uint32_t a0[4], a1[4];
-                    load_a(a0, sm + C::O_OB0 + ((q * C::OJP + jp) * 2) * 512 + lane * 16);
-                    load_a(a1, sm + C::O_OB0 + ((q * C::OJP + jp) * 2 + 1) * 512 + lane * 16);
+                    load_a(a0, abuf + ((kp0 + jp) * 2) * 512 + lane16);
+                    load_a(a1, abuf + ((kp0 + jp) * 2 + 1) * 512 + lane16);
+                    uint4 bw[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint4 bw = lds128(st + ((4 * w + i) * C::OJP + jp) * 512 + lane * 16);
-                        hmma(zz[i], a0, bw.x, bw.y);
-                        hmma(zz[i], a1, bw.z, bw.w);
-                    }
+                    for (int i = 0; i < 4; i++) bw[i] = lds128(st + (i * ojp + jp) * 512);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) hmma(zz[i], a0, bw[i].x, bw[i].y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) hmma(zz[i], a1, bw[i].z, bw[i].w);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_a(s_empty + 8 * (cnt & 1));
-            }
+                release(s_empty + bo);
+            };
+#pragma unroll
+            for (int q = 0; q < C::NQ_ZS; q++) out_gemm(q, C::OJP_ZS, sm + C::O_OB0, q * C::OJP_ZS);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int nt = 4 * w + i, c = 8 * nt + 2 * t4;
                 const float z0 = fmaxf(zz[i][0], 0.f), z1 = fmaxf(zz[i][1], 0.f), z2 = fmaxf(zz[i][2], 0.f), z3 = fmaxf(zz[i][3], 0.f);
-                sts64(sm + C::O_OB1 + (nt >> 1) * 512 + lane * 16 + (nt & 1) * 8, pack_h2(z0, z1), pack_h2(z2, z3));
-                if (last) {
+                sts64(sm + C::O_OB1 + (nt >> 1) * 512 + lane16 + (nt & 1) * 8, pack_h2(z0, z1), pack_h2(z2, z3));
+                if (DUMP) {
                     if (v0) { p.Zs[(size_t)b0 * A + c] = z0; p.Zs[(size_t)b0 * A + c + 1] = z1; }
                     if (v1) { p.Zs[(size_t)b1 * A + c] = z2; p.Zs[(size_t)b1 * A + c + 1] = z3; }
                 }
@@ -580,31 +644,16 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
             }
             bar_compute();
             if (tid == 0) TRACE(0, 21);
-            for (int q = 0; q < C::NQ_ZA; q++, cnt++) {
-                const uint32_t st = sm + C::O_RING + (cnt & 1) * C::LAYER_BYTES, fb = s_full + (cnt & 1) * 32, ph = (cnt >> 1) & 1;
-                mbar_wait_a(fb + 8 * (w >> 1), ph);
 #pragma unroll
-                for (int jp = 0; jp < C::OJP; jp++) {
-                    uint32_t a0[4], a1[4];
-                    load_a(a0, sm + C::O_OB1 + ((q * C::OJP + jp) * 2) * 512 + lane * 16);
-                    load_a(a1, sm + C::O_OB1 + ((q * C::OJP + jp) * 2 + 1) * 512 + lane * 16);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint4 bw = lds128(st + ((4 * w + i) * C::OJP + jp) * 512 + lane * 16);
-                        hmma(zz[i], a0, bw.x, bw.y);
-                        hmma(zz[i], a1, bw.z, bw.w);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_a(s_empty + 8 * (cnt & 1));
-            }
-            // logits (fp32) -> transposed buffer: row = utterance, 256 contiguous channels
+            for (int q = 0; q < C::NQ_ZA; q++) out_gemm(C::NQ_ZS + q, C::OJP_ZA, sm + C::O_OB1, q * C::OJP_ZA);
+            // 8 pieces = 4 slot pairs later: same slot, same barrier parity as before the output phase
+            // logits (fp32) -> transposed buffer: row = utterance, 256 contiguous classes
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int c = 32 * w + 8 * i + 2 * t4;
                 sts64(sm + C::O_LBUF + (g * LROW + c) * 4, __float_as_uint(zz[i][0]), __float_as_uint(zz[i][1]));
                 sts64(sm + C::O_LBUF + ((g + 8) * LROW + c) * 4, __float_as_uint(zz[i][2]), __float_as_uint(zz[i][3]));
-                if (last) {
+                if (DUMP) {
                     if (v0) { p.Za[(size_t)b0 * A + c] = zz[i][0]; p.Za[(size_t)b0 * A + c + 1] = zz[i][1]; }
                     if (v1) { p.Za[(size_t)b1 * A + c] = zz[i][2]; p.Za[(size_t)b1 * A + c + 1] = zz[i][3]; }
                 }
@@ -660,7 +709,7 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
                     const int ck = __shfl_sync(0xffffffffu, cntk, lf);
                     const int y = ball ? 8 * lf + (ck < 7 ? ck : 7) : A - 1;
                     const int b = tile * TU + 2 * w + r;
-                    if (last && b < B) {
+                    if (DUMP && b < B) {
                         const float inv = 1.f / total;
                         float prevv = 0.f;
 #pragma unroll
@@ -677,8 +726,12 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
                     }
                 }
             }
+            cp_async_wait_all();                       // the next sample's previous-index rows have landed
             bar_compute();
             if (tid == 0) TRACE(0, 23);
+            epar ^= 1;
+            if (++it0.slot == slots) it0.slot = 0;
+            it0.t++;
         }
         if (tid < TU && tile * TU + tid < B) { p.yCur[tile * TU + tid] = ys[tid]; p.yPrev[tile * TU + tid] = ys[TU + tid]; }
     }
@@ -690,7 +743,7 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
 // ------------------------------------------------------------------------------------------------ host side
 bool wn_lat_supported(int R_, int S, int A_, int L)
 {
-    return R_ == R && A_ == A && (S == 128 || S == 256) && L >= 1 && L <= MAXL;
+    return R_ == R && A_ == A && (S == 128 || S == 256) && L >= 4 && L <= MAXL;     // L >= 4: history prefetch runs 3 steps ahead
 }
 int wn_lat_tiles(int B) { return (B + TU - 1) / TU; }
 size_t wn_lat_image_bytes(int S, int L) { return lat_image(S, L).total; }
@@ -718,25 +771,42 @@ cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream)
 }
 
 // p.B = utterances of this run; engine_B = batch size the conditioning store / history ring were laid out for
+template <int S>
+static cudaError_t lat_launch_S(const WnParams& p, const unsigned char* im8, int grid, int ntiles_alloc, cudaStream_t stream, size_t* smem_out)
+{
+    const size_t smem = Cfg<S>::SMEM;
+    *smem_out = smem;
+    cudaError_t e;
+#define LAT_GO(DUMPV, TRCV, PP)                                                                                                    \
+    do {                                                                                                                           \
+        e = cudaFuncSetAttribute(wn_lat_kernel<S, DUMPV, TRCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        if (e != cudaSuccess) return e;                                                                                            \
+        wn_lat_kernel<S, DUMPV, TRCV><<<grid, NT, smem, stream>>>(PP, im8, ntiles_alloc);                                          \
+        e = cudaGetLastError();                                                                                                    \
+        if (e != cudaSuccess) return e;                                                                                            \
+    } while (0)
+    // a dumping launch = every sample but the last with the plain kernel, then the last one with the dumping variant
+    // (a continuation is bit-identical to one launch: the whole state lives in global memory between launches)
+    WnParams head = p, tail = p;
+    if (p.dump) { head.count = p.count - 1; head.dump = 0; tail.init_sample = p.init_sample + p.count - 1; tail.count = 1; }
+    if (head.count > 0) {
+        if (p.trace) LAT_GO(false, true, head); else LAT_GO(false, false, head);
+    }
+    if (p.dump) LAT_GO(true, false, tail);
+#undef LAT_GO
+    return cudaSuccess;
+}
+
 cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, cudaStream_t stream, WnLaunchInfo* info)
 {
     const int grid = wn_lat_tiles(p.B), ntiles_alloc = wn_lat_tiles(engine_B);
     const unsigned char* im8 = static_cast<const unsigned char*>(image);
+    size_t smem = 0;
     cudaError_t e;
-    size_t smem;
-    if (p.S == 256) {
-        smem = Cfg<256>::SMEM;
-        e = cudaFuncSetAttribute(wn_lat_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        wn_lat_kernel<256><<<grid, NT, smem, stream>>>(p, im8, ntiles_alloc);
-    } else if (p.S == 128) {
-        smem = Cfg<128>::SMEM;
-        e = cudaFuncSetAttribute(wn_lat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        wn_lat_kernel<128><<<grid, NT, smem, stream>>>(p, im8, ntiles_alloc);
-    } else {
-        return cudaErrorInvalidValue;
-    }
+    if (p.S == 256) e = lat_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);
+    else if (p.S == 128) e = lat_launch_S<128>(p, im8, grid, ntiles_alloc, stream, &smem);
+    else return cudaErrorInvalidValue;
+    if (e != cudaSuccess) return e;
     if (info) { info->kernel = 18; info->grid = grid; info->block = NT; info->smem_bytes = (int)smem; info->batch_per_cta = TU; info->cluster = 1; }
     return cudaGetLastError();
 }
