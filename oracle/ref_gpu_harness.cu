@@ -84,7 +84,9 @@ int main(int argc, char** argv)
     int rc = 4;
     const int prec = h[0], R = h[1], S = h[2], A = h[3];
     if (R == 64 && S == 256 && A == 256) rc = (prec == 16) ? run<half2, half, 64, 256, 256>(h, f.data(), out) : run<float, float, 64, 256, 256>(h, f.data(), out);
-    else fprintf(stderr, "unsupported shape (built for R64/S256/A256)\n");
+    else if (R == 64 && S == 128 && A == 256 && prec == 16) rc = run<half2, half, 64, 128, 256>(h, f.data(), out);      // BASELINE.json configs[1] (C2)
+    else if (R == 128 && S == 256 && A == 256 && prec == 32) rc = run<float, float, 128, 256, 256>(h, f.data(), out);  // BASELINE.json configs[3] (C4)
+    else fprintf(stderr, "unsupported shape (built for R64/S256/A256 fp16+fp32, R64/S128/A256 fp16, R128/S256/A256 fp32)\n");
     fclose(out);
     return rc;
 }
