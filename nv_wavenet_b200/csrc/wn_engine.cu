@@ -37,7 +37,7 @@ size_t wn_lat_ring_bytes(int L, int maxDil, int B);
 size_t wn_lat_cond_bytes(int L, int B, int N);
 cudaError_t wn_lat_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
 cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream);
-cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, cudaStream_t stream, WnLaunchInfo* info);
+cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, int variant, cudaStream_t stream, WnLaunchInfo* info);
 
 namespace {
 
@@ -91,6 +91,7 @@ struct nvwn_engine {
     bool tc_dirty = true;
     bool tc_mode = false;                    // decided once at creation: conditioning + history use the tiled layouts
     bool lat_mode = false;                   // decided once at creation: latency-mode kernel (fragment-ordered layouts); tc_image holds its weight image
+    int lat_variant = 16;                    // 16 = role-specialised (16 compute warps), 8 = symmetric 8-warp kernel (NVWN_LAT_WARPS, read once)
 
     float* lut_f = nullptr;                  // mu-law decode tables (nvwn_get_audio): A floats, then 2 x A int16 (wrap / saturate)
     unsigned long long* trace = nullptr;     // debug timeline (nvwn_debug_trace)
@@ -237,6 +238,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     {
         const int k = decide_fp16_kernel(dtype, impl, R, S, A, num_layers, batch_size);
         e->tc_mode = k == 1; e->lat_mode = k == 2;
+        if (const char* v = getenv("NVWN_LAT_WARPS")) e->lat_variant = atoi(v) == 8 ? 8 : 16;
     }
     ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(S, num_layers, batch_size, num_samples)
                  : e->lat_mode ? wn_lat_cond_bytes(num_layers, batch_size, num_samples) : Nz * L * Bz * 2 * R * td);
@@ -472,7 +474,7 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
                 CK(wn_lat_pack(e->tc_image, p, stream));
                 e->tc_dirty = false;
             }
-            CK(wn_launch_lat(p, e->tc_image, e->B, stream, &e->last));
+            CK(wn_launch_lat(p, e->tc_image, e->B, e->lat_variant, stream, &e->last));
         } else if (e->tc_mode) {
             if (batch_size != e->B)
                 return fail(NVWN_EINVAL, "nvwn_run_partial: the tensor-core path needs batch_size equal to the engine's batch size");

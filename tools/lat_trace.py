@@ -27,7 +27,7 @@ e.run(N, B, None); torch.cuda.synchronize()
 buf = np.zeros(3 * 1024, np.uint64)
 assert lib.nvwn_debug_trace(e._h, T, buf.ctypes.data, 1) == 0
 names = {1: "sample start (ys read)", 2: "x0 built", 10: "h exchanged", 11: "layer done (x exchanged)", 12: "cur+prev GEMM issued", 13: "gate done",
-         14: "res done", 15: "skip issued", 20: "relu(skip) exchanged", 21: "relu(Zs) exchanged", 22: "logits exchanged", 23: "sample done"}
+         14: "res done", 15: "skip issued", 16: "bg: h seen", 17: "bg: step start", 20: "relu(skip) exchanged", 21: "relu(Zs) exchanged", 22: "logits exchanged", 23: "sample done"}
 ev = []
 for role in range(3):
     for v in buf[role * 1024:(role + 1) * 1024]:
@@ -36,7 +36,7 @@ for role in range(3):
             ev.append((v & 0xFFFFFFFFFFFF, role, v >> 48))
 ev.sort()
 t0 = ev[0][0]
-prev = {0: t0, 2: t0}
+prev = {0: t0, 1: t0, 2: t0}
 for clk, role, tag in ev:
     nm = names.get(tag, ("prod: layer %d issued" % (tag - 100)) if 100 <= tag < 200 else ("prod: out load %d issued" % (tag - 200)) if tag >= 200 else str(tag))
     print(f"{clk - t0:8d} (+{clk - prev[role]:6d})  role{role}  {nm}")
