@@ -31,8 +31,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-MODEL = dict(L=20, R=64, S=256, A=256, max_dilation=512)
+# BASELINE.json configs: C3 = configs[2] (the headline the metric is quoted on), C2 = configs[1], C4 = configs[3]
+CONFIGS = {
+    "C3": dict(L=20, R=64, S=256, A=256, max_dilation=512, batch=64, dtype="fp16"),
+    "C2": dict(L=20, R=64, S=128, A=256, max_dilation=512, batch=8, dtype="fp16"),
+    "C4": dict(L=30, R=128, S=256, A=256, max_dilation=512, batch=16, dtype="fp32"),
+}
+MODEL = dict(CONFIGS["C3"])
 SEED = 20260922
+
+
+def metric_name():
+    """One string for both arms (the driver divides the two lines only if it is identical); precision is in `dtype`."""
+    return f"samples/s (kHz/utterance x batch) {MODEL['L']}L R{MODEL['R']}/S{MODEL['S']}/A{MODEL['A']}"
 
 
 def weight_bytes(L, R, S, A, T):
@@ -164,7 +175,7 @@ def run_reference(args, rank, world):
     ms = (time.perf_counter() - t0) * 1e3 / args.steps
     value = statistics.mean(rates)
     line = {
-        "impl": "reference", "metric": "samples/s (kHz/utterance x batch) 20L R64/S256/A256", "value": value, "unit": "samples/s",
+        "impl": "reference", "metric": metric_name(), "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, batch),
@@ -177,12 +188,79 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, batch):
-    return {"workload": f"C3: WaveNet autoregressive inference, 20 layers R64/S256/A256 maxDilation512, "
-                        f"batch {args.batch}/GPU ({batch} total) x {args.samples} samples",
+    return {"workload": f"{args.config}: WaveNet autoregressive inference, {MODEL['L']} layers R{MODEL['R']}/S{MODEL['S']}/A{MODEL['A']} "
+                        f"maxDilation{MODEL['max_dilation']}, batch {args.batch}/GPU ({batch} total) x {args.samples} samples",
+            "weights": "random N(0, sigma) per matrix (lively gates), not the reference test's U(-0.25/R, 0.25/R): no effect on speed",
             "batch_per_gpu": args.batch, "global_batch": batch, "samples_per_utterance": args.samples,
             "parallelism": f"batch-shard x{args.gpus} (no per-step collective)",
             "l2_policy": "conditioning stream (>5 GB/step) exceeds L2; weights are L2/SMEM-resident by design",
             **({"note": os.environ["NVWN_BENCH_NOTE"]} if os.environ.get("NVWN_BENCH_NOTE") else {})}
+
+
+# --------------------------------------------------------------------------- extras (single-GPU runs only)
+def batch_sweep(nw, torch, args, dtype, T, peak, alg, n_samples=4000):
+    """Kernel-only rate at 1x, 2x, 4x the configured batch (same model, shorter utterances): where the normalised roofline
+    fraction crosses 0.6 is driver-observable."""
+    import numpy as np
+    L, R, S, A, md = MODEL["L"], MODEL["R"], MODEL["S"], MODEL["A"], MODEL["max_dilation"]
+    w = model_weights(SEED, L, R, S, A)
+    out = []
+    for mult in (1, 2, 4):
+        B = args.batch * mult
+        eng = nw.NVWavenetInfer(L, md, B, n_samples, R=R, S=S, A=A, dtype=dtype)
+        eng.load(w)
+        gen = torch.Generator(device="cuda"); gen.manual_seed(SEED + B)
+        chunk = max(1, min(n_samples, (256 << 20) // (L * B * 2 * R * 4)))
+        for s0 in range(0, n_samples, chunk):
+            n = min(chunk, n_samples - s0)
+            eng.set_conditioning(torch.randn((n, L, B, 2 * R), generator=gen, device="cuda", dtype=torch.float32) * 0.5, s0, n)
+        eng.set_selectors(torch.rand((n_samples, B), generator=gen, device="cuda", dtype=torch.float32))
+        best = None
+        for _ in range(3):
+            eng.reset_history()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); eng.run(n_samples, B, None); e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        rate = B * n_samples / (best * 1e-3)
+        out.append({"batch": B, "samples": n_samples, "khz_per_utterance": n_samples / best, "samples_per_s": rate,
+                    "roofline_frac": rate * alg / 1e9 / peak, "kernel": eng.launch_info()["kernel"], "grid": eng.launch_info()["grid"]})
+        eng.close()
+    return out
+
+
+def reference_gpu_kernels(args, our_khz, n_samples=600):
+    """The reference's OWN CUDA kernels (oracle/_ref/ref_gpu_harness: unmodified nv_wavenet.cuh rebuilt for sm_100a), same model,
+    same batch, same box, timed like nv_wavenet_perf.cu:67-87 -- the GPU baseline next to the headline.  Test infrastructure:
+    a separate process; nothing of it is on our path."""
+    try:
+        from oracle import ref_gpu
+        if not ref_gpu.available():
+            return {"unavailable": "oracle/_ref/ref_gpu_harness not built"}
+        import numpy as np
+        L, R, S, A, md = MODEL["L"], MODEL["R"], MODEL["S"], MODEL["A"], MODEL["max_dilation"]
+        w = model_weights(SEED, L, R, S, A)
+        for k in w:                                     # the reference accumulates in fp16: keep its arithmetic finite
+            w[k] = (w[k] * np.float32(0.5)).astype(np.float32)
+        g = np.random.Generator(np.random.PCG64(SEED))
+        B = args.batch
+        w["Lh"] = (g.standard_normal((n_samples, L, B, 2 * R), dtype=np.float32) * np.float32(0.25))
+        w["selectors"] = g.random((n_samples, B), dtype=np.float32)
+        prec = 16 if args.dtype == "fp16" else 32
+        out = {"samples": n_samples, "batch": B, "ours_khz_per_utterance": our_khz}
+        best = 0.0
+        for mode, name in ((1, "single_block"), (2, "dual_block"), (3, "persistent"), (4, "manyblock")):
+            try:
+                r = ref_gpu.run(w, prec, R, S, A, L, md, B, n_samples, mode=mode, chunk=2048, reps=2, timeout=120)
+                out[name] = {"khz_per_utterance": r["khz"], "samples_per_s": r["samples_per_s"]}
+                best = max(best, r["khz"])
+            except Exception as ex:       # noqa: BLE001
+                out[name] = {"error": str(ex).strip()[-160:]}
+        out["best_reference_khz_per_utterance"] = best or None
+        out["ours_over_best_reference"] = (our_khz / best) if best else None
+        return out
+    except Exception as ex:               # noqa: BLE001
+        return {"unavailable": str(ex)[:200]}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -215,6 +293,32 @@ def run_ours(args, rank, world, local_rank):
         dist.broadcast(blob, 0)
         eng.weights_updated()
 
+    stream = torch.cuda.current_stream()
+    # ---- every rank must hold rank 0's weights: all ranks generate the SAME short input (rank 0's seed), run it, and the
+    # CRCs of the sampled indices are compared (a rank on a zero / stale blob would run at the same speed but sample differently)
+    import zlib
+    V = min(N, 256)
+    gen0 = torch.Generator(device="cuda"); gen0.manual_seed(SEED)
+    eng.set_conditioning(torch.randn((V, L, B, 2 * R), generator=gen0, device="cuda", dtype=torch.float32) * 0.5, 0, V)
+    eng.set_selectors(torch.rand((N, B), generator=gen0, device="cuda", dtype=torch.float32))
+    eng.reset_history()
+    eng._samples_per_chunk = V
+    eng.run_partial(0, N, B, None, 1, False, stream)
+    eng._samples_per_chunk = 0
+    yv = np.zeros((B, N), np.int32)
+    eng.get_yout(yv, 0, V, stream); torch.cuda.synchronize()
+    crc = zlib.crc32(np.ascontiguousarray(yv[:, :V]).tobytes())
+    crcs = [crc]
+    if dist:
+        tcrc = torch.tensor([crc], device="cuda", dtype=torch.int64)
+        allc = [torch.zeros_like(tcrc) for _ in range(world)]
+        dist.all_gather(allc, tcrc)
+        crcs = [int(c.item()) for c in allc]
+    verify = {"yout_crc_equal_across_ranks": len(set(crcs)) == 1, "yout_crc": [f"{c:08x}" for c in crcs], "samples": V,
+              "distinct_indices": int(len(np.unique(yv[:, :V])))}
+    if not verify["yout_crc_equal_across_ranks"]:
+        raise RuntimeError(f"ranks disagree on the same input (weight broadcast broken?): {verify}")
+
     # synthetic conditioning generated on the device, chunk by chunk, in the kernel's dtype via the public setter
     gen = torch.Generator(device="cuda"); gen.manual_seed(SEED + 17 * rank)
     chunk = max(1, min(N, (256 << 20) // (L * B * 2 * R * 4)))
@@ -227,7 +331,6 @@ def run_ours(args, rank, world, local_rank):
     sel = torch.rand((N, B), generator=gen, device="cuda", dtype=torch.float32)
     eng.set_selectors(sel)
     y_dev = torch.zeros((B, N), dtype=torch.int32, device="cuda")
-    stream = torch.cuda.current_stream()
 
     def step():
         eng.reset_history()
@@ -318,15 +421,21 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     alg = algorithmic_bytes(L, R, S, A, T)
     achieved = B * N * alg / (kernel_ms * 1e-3) / 1e9                # one launch = one step of one GPU
-    traffic = None
+    # DRAM traffic is not measured on this run: the committed ncu capture (profiles/ncu_summary.json) gives bytes per unit
+    # for a shorter launch of the same kernel; the figure scaled to this launch is reported as an extrapolation
+    traffic_x = None
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_unit") * B * N      # ncu dram read+write bytes, scaled to this launch
+            pj = json.load(open(prof))
+            if pj.get("config") == args.config and pj.get("kernel_id") == info["kernel"]:
+                traffic_x = {"value": pj["dram_bytes_per_unit"] * B * N, "dram_bytes_per_unit": pj["dram_bytes_per_unit"],
+                             "capture_samples": pj.get("capture_samples"), "capture_batch": pj.get("capture_batch"), "source": "profiles/ncu_summary.json"}
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": {16: "wn_stream_kernel", 17: "wn_tc_kernel"}.get(info["kernel"], str(info["kernel"])),
+            traffic_x = None
+    kname = {16: "wn_stream_kernel", 17: "wn_tc_kernel", 18: "wn_lat_kernel"}.get(info["kernel"], str(info["kernel"]))
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "traffic_extrapolated": traffic_x, "peak_source": peak_src, "kernel": kname,
                 "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_unit": alg, "units_per_launch": B * N,
                 "note": "BASELINE.md §2 normalisation: one read of all weights per utterance-sample; weights are re-used across the batch "
                         "on chip, so frac may exceed 1 -- real DRAM traffic is `traffic`"}
@@ -338,14 +447,18 @@ def run_ours(args, rank, world, local_rank):
                    "sample": f"nv_wavenet_reference.cpp (unmodified, -O2): batch {B} sharded over {cores} processes, {args.cpu_samples} samples each ({wall:.1f}s wall)"}
         except Exception as ex:       # noqa: BLE001
             cpu = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+    extra = {"verify": verify}
+    if world == 1 and not args.no_extra:
+        extra["batch_sweep"] = batch_sweep(nw, torch, args, dtype, T, peak, alg)
+        extra["reference_gpu_kernels"] = reference_gpu_kernels(args, N / (elapsed_ms / args.steps))
     line = {
-        "metric": "samples/s (kHz/utterance x batch) 20L R64/S256/A256 fp16", "value": value, "unit": "samples/s",
+        "metric": metric_name(), "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == nw.FP16 else "f32",
         "data": "synthetic", "config": workload_config(args, world * B),
         "khz_per_utterance": N / (elapsed_ms / args.steps), "clocks": clk, "e2e": e2e, "gpu_launches": launches,
         "launch": {k: info[k] for k in ("kernel", "grid", "block", "smem_bytes", "batch_per_cta")},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if dist:
@@ -358,14 +471,21 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS), help="BASELINE.json configuration (C3 = headline)")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU (default: the configuration's)")
     ap.add_argument("--samples", type=int, default=16000)
-    ap.add_argument("--dtype", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--dtype", default=None, choices=["fp16", "fp32"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the batch sweep and the reference-GPU-kernel runs")
     ap.add_argument("--cpu-samples", type=int, default=96, help="samples per utterance of the bounded CPU-reference leg")
     ap.add_argument("--e2e-chunk", type=int, default=1000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    MODEL.clear(); MODEL.update(CONFIGS[args.config])
+    if args.batch is None:
+        args.batch = MODEL["batch"]
+    if args.dtype is None:
+        args.dtype = MODEL["dtype"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -377,18 +497,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    try:
-        run_ours(args, rank, world, local_rank)
-    except Exception as exc:  # noqa: BLE001
-        # A device-side failure (the kernel's bounded mbarrier waits trap instead of hanging) poisons the CUDA context.
-        # Single-process runs re-measure ONCE in a fresh process with the most exercised tile shape of the kernel and say
-        # so in config.note; anything else (multi-rank, second failure) is fatal.
-        if world == 1 and not os.environ.get("NVWN_BENCH_NOTE"):
-            print(f"bench.py: run failed ({type(exc).__name__}: {exc}); re-measuring once with NVWN_TC_TILE=64", file=sys.stderr, flush=True)
-            env = dict(os.environ, NVWN_TC_TILE="64",
-                       NVWN_BENCH_NOTE=f"re-measured with 64-utterance tiles after a failed first attempt ({type(exc).__name__})")
-            os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env)
-        raise
+    # a device-side failure (the kernels' bounded mbarrier waits trap instead of hanging) is fatal: rc != 0, no re-measurement
+    run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -47,6 +47,19 @@ cudaError_t wn_f32_to_f16(__half* dst, const float* src_dev, size_t n, cudaStrea
     return cudaGetLastError();
 }
 
+__global__ void f16_to_f32_kernel(float* __restrict__ dst, const __half* __restrict__ src, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __half2float(src[i]);
+}
+cudaError_t wn_f16_to_f32(float* dst, const __half* src_dev, size_t n, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    f16_to_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dst, src_dev, n);
+    return cudaGetLastError();
+}
+
 cudaError_t wn_fill_int(int* dst, int value, size_t n, cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;

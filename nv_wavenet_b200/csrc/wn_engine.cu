@@ -37,7 +37,9 @@ size_t wn_lat_ring_bytes(int L, int maxDil, int B);
 size_t wn_lat_cond_bytes(int L, int B, int N);
 cudaError_t wn_lat_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
 cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream);
-cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, int variant, cudaStream_t stream, WnLaunchInfo* info);
+cudaError_t wn_lat_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
+cudaError_t wn_tc_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream);
+cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, cudaStream_t stream, WnLaunchInfo* info);
 
 namespace {
 
@@ -91,7 +93,6 @@ struct nvwn_engine {
     bool tc_dirty = true;
     bool tc_mode = false;                    // decided once at creation: conditioning + history use the tiled layouts
     bool lat_mode = false;                   // decided once at creation: latency-mode kernel (fragment-ordered layouts); tc_image holds its weight image
-    int lat_variant = 16;                    // 16 = role-specialised (16 compute warps), 8 = symmetric 8-warp kernel (NVWN_LAT_WARPS, read once)
 
     float* lut_f = nullptr;                  // mu-law decode tables (nvwn_get_audio): A floats, then 2 x A int16 (wrap / saturate)
     unsigned long long* trace = nullptr;     // debug timeline (nvwn_debug_trace)
@@ -238,7 +239,6 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     {
         const int k = decide_fp16_kernel(dtype, impl, R, S, A, num_layers, batch_size);
         e->tc_mode = k == 1; e->lat_mode = k == 2;
-        if (const char* v = getenv("NVWN_LAT_WARPS")) e->lat_variant = atoi(v) == 8 ? 8 : 16;
     }
     ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(S, num_layers, batch_size, num_samples)
                  : e->lat_mode ? wn_lat_cond_bytes(num_layers, batch_size, num_samples) : Nz * L * Bz * 2 * R * td);
@@ -474,7 +474,7 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
                 CK(wn_lat_pack(e->tc_image, p, stream));
                 e->tc_dirty = false;
             }
-            CK(wn_launch_lat(p, e->tc_image, e->B, e->lat_variant, stream, &e->last));
+            CK(wn_launch_lat(p, e->tc_image, e->B, stream, &e->last));
         } else if (e->tc_mode) {
             if (batch_size != e->B)
                 return fail(NVWN_EINVAL, "nvwn_run_partial: the tensor-core path needs batch_size equal to the engine's batch size");
@@ -580,6 +580,27 @@ int nvwn_get_audio(nvwn_engine* e, float* audio_f32, short* audio_i16, int offse
         cudaFree(tmp);
     }
     if (ce != cudaSuccess) return fail((int)ce, std::string("nvwn_get_audio: ") + cudaGetErrorString(ce));
+    return 0;
+}
+
+// debug only (not part of the public ABI): the engine's conditioning store for samples [first_sample, first_sample + num_samples),
+// converted back to fp32 [num_samples][L][B][2R] whatever the kernel-native layout (plain / tiled fp16 / fragment order) is
+int nvwn_debug_get_conditioning(nvwn_engine* e, float* out, int first_sample, int num_samples)
+{
+    if (!e || !out) return fail(NVWN_EINVAL, "nvwn_debug_get_conditioning: NULL argument");
+    if (first_sample < 0 || num_samples < 0 || first_sample + num_samples > e->N) return fail(NVWN_EINVAL, "nvwn_debug_get_conditioning: range out of bounds");
+    const size_t per = (size_t)e->L * e->B * 2 * e->R, n = per * num_samples;
+    if (n == 0) return 0;
+    float* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, n * sizeof(float)));
+    cudaError_t ce;
+    if (e->lat_mode) ce = wn_lat_cond_readback(tmp, e->Lh, first_sample, num_samples, e->L, e->B, 0);
+    else if (e->tc_mode) ce = wn_tc_cond_readback(tmp, e->Lh, first_sample, num_samples, e->S, e->L, e->B, 0);
+    else if (e->dtype == NVWN_FP16) ce = wn_f16_to_f32(tmp, static_cast<const __half*>(e->Lh) + (size_t)first_sample * per, n, 0);
+    else ce = cudaMemcpyAsync(tmp, static_cast<const float*>(e->Lh) + (size_t)first_sample * per, n * sizeof(float), cudaMemcpyDeviceToDevice, 0);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, tmp, n * sizeof(float), cudaMemcpyDefault);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) return fail((int)ce, std::string("nvwn_debug_get_conditioning: ") + cudaGetErrorString(ce));
     return 0;
 }
 

@@ -212,6 +212,24 @@ __global__ void lat_cond_kernel(unsigned char* __restrict__ dst, const float* __
     }
 }
 
+// inverse of lat_cond_kernel (debug / tests): conditioning store -> fp32 [n][L][B][2R]
+__global__ void lat_cond_readback_kernel(float* __restrict__ dst, const unsigned char* __restrict__ src, int first_sample, int nsamples, int L, int B, int ntiles)
+{
+    const size_t total = (size_t)nsamples * L * B * 64;            // one thread per channel pair
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c2 = (int)(i & 63);
+        const size_t row = i >> 6;                                  // (s * L + l) * B + b
+        const int b = (int)(row % B);
+        const size_t sl = row / B;
+        const int tile = b / TU, r = b % TU, g = r & 7, hi = r >> 3;
+        const int sig = c2 >= 32, cc = (c2 & 31) * 2, w = cc >> 3, t = (cc & 7) >> 1;
+        const size_t off = (((size_t)first_sample * L + sl) * ntiles + tile) * 4096 + (size_t)(w * 32 + g * 4 + t) * 16 + (size_t)(2 * sig + hi) * 4;
+        const __half2 v = *reinterpret_cast<const __half2*>(src + off);
+        dst[row * 128 + sig * 64 + cc] = __low2float(v);
+        dst[row * 128 + sig * 64 + cc + 1] = __high2float(v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pack
 // blob (fp16, column-major M x K matrices as uploaded) -> weight image in mma.m16n8k16 B-fragment order.
 // Element (n-tile nt, k-step pair jp, lane = 4 g + t) of a matrix W[M][K] is the uint4
@@ -744,511 +762,6 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
 #undef TRACE
 }
 
-// ================================================================================================ role-specialised variant
-// Same data flow, twice the warps: the serial instruction stream of a warp -- not the tensor pipe (27 % busy) nor the weight
-// stream -- bounded the 8-warp kernel above, so the work of a layer step is split by ROLE:
-//   warps 0-7   "chain":       cur GEMM -> gate -> [h tile] -> prev GEMM of the next step -> res GEMM -> [x tile, history ring]
-//   warps 8-15  "background":  skip GEMM (one step behind, off the chain), staging of the dilated history x[t-d] three steps
-//                              ahead (cp.async into a 3-slot shared-memory ring, completion on an mbarrier), L2 prefetch of Lh
-//   warp  15    is also the TMA producer: every wait of that warp on an mbarrier is a polling loop that issues whatever ring
-//               pieces have become free (all its other blocking points are barriers nobody can be waiting behind for a piece)
-// all 16 compute warps share the output GEMMs (2 n-tiles each) and the softmax (one utterance per warp).
-// h goes chain -> background through a double-buffered tile and a pair of mbarriers.
-constexpr int NT2 = 16 * 32;               // 16 warps -> 128 registers per thread; the TMA producer is a duty of warp 15
-
-template <int S>
-struct Cfg2 {
-    using C = Cfg<S>;
-    static constexpr uint32_t O_RING1 = 0, O_RING2 = 2 * C::SLOT1;
-    static constexpr uint32_t O_EMB = O_RING2 + 2 * C::SLOT2;
-    static constexpr uint32_t O_BOUT = O_EMB + A * EROW * 4;
-    static constexpr uint32_t O_EPBUF = O_BOUT + (S + 2 * A) * 4;
-    static constexpr uint32_t O_PST = O_EPBUF + 2 * TU * EROW * 4;          // 3 x 2 KB: staged history tiles (A-fragment order)
-    static constexpr uint32_t O_OB0 = O_PST + 3 * 2048;
-    static constexpr uint32_t O_OB1 = O_OB0 + (S / 16) * 512;
-    static constexpr uint32_t O_LBUF = O_OB1 + (A / 16) * 512;              // transposed logits; its first 6 KB double as ...
-    static constexpr uint32_t O_XBUF = O_LBUF, O_HBUF = O_LBUF + 2048;      // ... the x tile and the two h tiles (dead in the tail)
-    static constexpr uint32_t O_DIL = O_LBUF + TU * LROW * 4;
-    static constexpr uint32_t O_YS = O_DIL + MAXL * 4;
-    static constexpr uint32_t O_BAR = O_YS + 2 * TU * 4;
-    static constexpr uint32_t SMEM = O_BAR + 16 * 8;
-};
-
-__device__ __forceinline__ void bar_arrive_id(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_sync_id(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
-// the mbarrier receives one arrival when all cp.async issued so far by this thread have landed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <int S, bool DUMP, bool TRC>
-__global__ void __launch_bounds__(NT2, 1) wn_lat2_kernel(const WnParams p, const unsigned char* __restrict__ img, const int ntiles_alloc)
-{
-    using C = Cfg<S>;
-    using M = Cfg2<S>;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const uint32_t sm = smem_u32(smem_raw);
-    const int L = p.L, B = p.B;
-    const LatImage im = lat_image(S, L);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
-    const int slots = p.maxDil + 1;
-    const int t_begin = p.init_sample, t_end = p.init_sample + p.count;
-    const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
-
-    const uint32_t s_full = sm + M::O_BAR, s_empty = s_full + 32, s_pfull = s_full + 64, s_hrdy = s_full + 88;     // [4], [4], [3], [2]
-    int* dil = reinterpret_cast<int*>(smem_raw + M::O_DIL);
-    int* ys = reinterpret_cast<int*>(smem_raw + M::O_YS);
-    float* s_bout = reinterpret_cast<float*>(smem_raw + M::O_BOUT);
-    constexpr int NQ = C::NQ_ZS + C::NQ_ZA;
-    static_assert(NQ == 8, "the ring bookkeeping assumes 8 output pieces per sample");
-    constexpr int NCOMP = 512;                         // threads of the 16 compute warps
-
-    unsigned long long* trc = (TRC && p.trace && blockIdx.x == 0) ? p.trace : nullptr;
-    int trn = 0;
-    const int tr_t = p.trace_t & 0xFFFF;
-#define TRACE(role, tag) do { if (TRC && trc && t == tr_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
-
-    if (tid == 0) {
-        for (int i = 0; i < 4; i++) { mbar_init_a(s_full + 8 * i, 1); mbar_init_a(s_empty + 8 * i, 16); }
-        for (int i = 0; i < 3; i++) mbar_init_a(s_pfull + 8 * i, 128);
-        mbar_init_a(s_hrdy, 8); mbar_init_a(s_hrdy + 8, 8);
-        fence_mbar_init();
-        int d = 1;
-        for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; }
-    }
-    {
-        const uint32_t* ec = static_cast<const uint32_t*>(p.embCur);
-        for (int i = tid; i < A * 32; i += NT2) sts32(sm + M::O_EMB + ((i >> 5) * EROW + (i & 31)) * 4, ec[i]);
-        for (int i = tid; i < S; i += NT2) s_bout[i] = gbias[im.b_skpre + (size_t)(L - 1) * S + i];
-        for (int i = tid; i < A; i += NT2) { s_bout[S + i] = gbias[im.b_bzs + i]; s_bout[S + A + i] = gbias[im.b_bza + i]; }
-        if (tid < TU) {
-            const int b = tile * TU + tid;
-            ys[tid] = b < B ? p.yCur[b] : 128;
-            ys[TU + tid] = b < B ? p.yPrev[b] : 128;
-        }
-    }
-    __syncthreads();
-
-    // =================================================================== 16 compute warps
-    const bool chain = warp < 8;
-    const int w = warp & 7;                            // index inside the role
-    const int g = lane >> 2, t4 = lane & 3;
-    const int b0 = tile * TU + g, b1 = b0 + 8;
-    const bool v0 = b0 < B, v1 = b1 < B;
-    const uint32_t cstride = (uint32_t)ntiles_alloc * 4096u, rstride = (uint32_t)ntiles_alloc * 2048u;
-    const unsigned char* gcond_tile = static_cast<const unsigned char*>(p.Lh) + (size_t)tile * 4096;
-    unsigned char* gring_tile = static_cast<unsigned char*>(p.ring) + (size_t)tile * 2048;
-    const uint32_t lane16 = (uint32_t)lane * 16;
-    const int jw = w >> 1, hw = w & 1;
-    const uint32_t xchg = (uint32_t)(jw * 512 + hw * 8) + lane16;
-    const int cw = 8 * w + 2 * t4;
-    const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16;
-    const uint32_t o_res = (uint32_t)(w * 2) * 512 + lane16, o_skip = 8192u + (uint32_t)(w * C::NSK * 2) * 512 + lane16;
-    const uint32_t o_out = (uint32_t)(2 * warp) * 512;                 // output pieces: this warp's two n-tiles (x OJP, + lane16)
-    auto advance = [&](StepIt& it) { if (++it.l == L) { it.l = 0; it.t++; if (++it.slot == slots) it.slot = 0; } };
-    auto release = [&](uint32_t bar) { __syncwarp(); if (lane == 0) mbar_arrive_a(bar); };
-
-    // ---- chain state
-    uint32_t xa[4][4];
-    uint4 cbA = make_uint4(0, 0, 0, 0), cbB = make_uint4(0, 0, 0, 0);
-    float accp[2][4];
-    float2 brn = make_float2(0.f, 0.f), br_next = make_float2(0.f, 0.f);
-    float4 bh_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    float xres[4] = {0.f, 0.f, 0.f, 0.f};
-    const unsigned char* cptr = gcond_tile + (size_t)(w * 32 + lane) * 16 + (size_t)t_begin * L * cstride;   // conditioning of step it3
-    const float* gbl = gbias + im.b_layer + (size_t)(w * 4 + t4) * 8;
-    StepIt it1{t_begin, 0, 0}, it3{t_begin, 0, 0};
-    // ---- background state
-    float sk[C::NSK][4];
-#pragma unroll
-    for (int i = 0; i < C::NSK; i++) sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
-    StepIt itp{t_begin, 0, t_begin % slots};           // step whose history tile is staged next
-    uint32_t pcnt = 0;                                 // staged tiles so far (slot = pcnt % 3)
-    const unsigned char* cpf = gcond_tile + (size_t)t_begin * L * cstride;                                   // L2 prefetch cursor (whole tile)
-
-    // ---- TMA producer duty of warp 15: ring pieces in consumption order (per sample: [Wcur|Wprev], [Wres|Wskip] per layer, then
-    // the 8 output pieces); service() issues every piece whose slot has been released, without ever blocking
-    const bool producer = warp == 15;
-    uint32_t ppc = 0;                                  // pieces issued so far
-    int ppi = 0;                                       // index of the next piece inside its sample
-    int ppt = t_begin;
-    const int pieces_per_sample = 2 * L + NQ;
-    auto service = [&]() {
-        while (ppt < t_end) {
-            const uint32_t idx = (ppc >> 1) & 1, bo = ((ppc & 1) * 2 + idx) * 8;
-            if (!mbar_test_a(s_empty + bo, ((ppc >> 2) & 1) ^ 1)) break;
-            if (lane == 0) {
-                const unsigned char* src;
-                uint32_t bytes;
-                if (ppi < 2 * L) {
-                    src = img + (size_t)(ppi >> 1) * im.layer_bytes + ((ppi & 1) ? C::P1_BYTES : 0);
-                    bytes = (ppi & 1) ? C::P2_BYTES : C::P1_BYTES;
-                } else {
-                    const int q = ppi - 2 * L;
-                    src = q < C::NQ_ZS ? img + im.off_zs + (size_t)q * C::ZS_PIECE : img + im.off_za + (size_t)(q - C::NQ_ZS) * C::ZA_PIECE;
-                    bytes = q < C::NQ_ZS ? C::ZS_PIECE : C::ZA_PIECE;
-                }
-                const uint32_t dst = (ppc & 1) ? sm + M::O_RING2 + idx * C::SLOT2 : sm + M::O_RING1 + idx * C::SLOT1;
-                mbar_expect_a(s_full + bo, bytes);
-                tma_load_a(dst, src, bytes, s_full + bo);
-                if (TRC && trc && ppt == tr_t && trn < 1023) trc[2 * 1024 + trn++] = ((unsigned long long)(ppi < 2 * L ? 100 + (ppi >> 1) : 200 + ppi - 2 * L) << 48) | (clock64() & 0xFFFFFFFFFFFFull);
-            }
-            ppc++;
-            if (++ppi == pieces_per_sample) { ppi = 0; ppt++; }
-        }
-    };
-    // wait on an mbarrier; warp 15 keeps the ring fed while it waits
-    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
-        if (producer) {
-            uint32_t spins = 0;
-            while (!mbar_test_a(bar, parity)) { service(); if (++spins > (1u << 22)) lat_timeout(bar, parity); }
-        } else {
-            mbar_wait_a(bar, parity);
-        }
-    };
-
-    // background warps 8-11: stage the history tile of step `itp` (128 threads x 16 B; zeros before the utterance starts)
-    auto stage_history = [&]() {
-        const uint32_t slot3 = pcnt % 3;
-        if (w < 4) {
-            const int d = dil[itp.l];
-            const uint32_t dst = sm + M::O_PST + slot3 * 2048 + (uint32_t)(w * 32 + lane) * 16;
-            if (itp.t >= t_end || itp.t < d) {
-                sts128(dst, make_uint4(0, 0, 0, 0));
-                mbar_arrive_a(s_pfull + 8 * slot3);
-            } else {
-                int sl = itp.slot - d; if (sl < 0) sl += slots;
-                cp_async16(dst, gring_tile + (size_t)((uint32_t)(sl * L + itp.l) * rstride) + (size_t)(w * 32 + lane) * 16);
-                cp_async_arrive_noinc(s_pfull + 8 * slot3);
-            }
-        }
-        pcnt++;
-        advance(itp);
-    };
-    // chain: accp <- (Bh + Lh) + Wprev . x[t-d] for the coming step it1 (its history tile is staged tile number `pn`)
-    uint32_t pn = 0;
-    auto prep = [&](uint4& cb, const uint32_t p1, const bool from_global) {
-        brn = br_next;
-        {
-            const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
-            accp[0][0] = bh_next.x + c0.x; accp[0][1] = bh_next.y + c0.y; accp[0][2] = bh_next.x + c1.x; accp[0][3] = bh_next.y + c1.y;
-            accp[1][0] = bh_next.z + c2.x; accp[1][1] = bh_next.w + c2.y; accp[1][2] = bh_next.z + c3.x; accp[1][3] = bh_next.w + c3.y;
-        }
-        const uint32_t slot3 = pn % 3;
-        if (it1.t < t_end) {
-            uint4 bt0, bg0, bt1, bg1;
-            if (from_global) {
-                const unsigned char* gp = img + (size_t)(L - 1) * im.layer_bytes + C::W_PREV;
-                bt0 = ldg_nc_v4(gp + o_t0); bg0 = ldg_nc_v4(gp + o_g0); bt1 = ldg_nc_v4(gp + o_t0 + 512); bg1 = ldg_nc_v4(gp + o_g0 + 512);
-            } else {
-                bt0 = lds128(p1 + C::W_PREV + o_t0); bg0 = lds128(p1 + C::W_PREV + o_g0);
-                bt1 = lds128(p1 + C::W_PREV + o_t0 + 512); bg1 = lds128(p1 + C::W_PREV + o_g0 + 512);
-            }
-            mbar_wait_a(s_pfull + 8 * slot3, (pn / 3) & 1);
-            uint32_t pb[4][4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) load_a(pb[j], sm + M::O_PST + slot3 * 2048 + j * 512 + lane16);
-            float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
-            hmma(accp[0], pb[0], bt0.x, bt0.y); hmma(accp[1], pb[0], bg0.x, bg0.y); hmma(u0, pb[2], bt1.x, bt1.y); hmma(u1, pb[2], bg1.x, bg1.y);
-            hmma(accp[0], pb[1], bt0.z, bt0.w); hmma(accp[1], pb[1], bg0.z, bg0.w); hmma(u0, pb[3], bt1.z, bt1.w); hmma(u1, pb[3], bg1.z, bg1.w);
-#pragma unroll
-            for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
-        }
-        pn++;
-        {   // conditioning of step it3 -> cb
-            const unsigned char* src = cptr;
-            cptr += cstride;
-            cb = it3.t < t_end ? ldg_nc_v4(src) : make_uint4(0, 0, 0, 0);
-        }
-        advance(it1); advance(it3);
-        bh_next = *reinterpret_cast<const float4*>(gbl + it1.l * 256);
-        br_next = *reinterpret_cast<const float2*>(gbl + it1.l * 256 + 4);
-    };
-
-    // ---------------- prologue
-    StepIt it0{t_begin, 0, t_begin % slots};
-    if (chain) {
-        const uint32_t* ep = static_cast<const uint32_t*>(p.embPrev);
-        sts32(sm + M::O_EPBUF + (g * EROW + 4 * w + t4) * 4, ep[ys[TU + g] * 32 + 4 * w + t4]);
-        sts32(sm + M::O_EPBUF + ((g + 8) * EROW + 4 * w + t4) * 4, ep[ys[TU + g + 8] * 32 + 4 * w + t4]);
-        it1 = it0; it3 = it0;
-        cbA = ldg_nc_v4(cptr); cptr += cstride;                                   // step 0
-        { StepIt i1 = it0; advance(i1); cbB = i1.t < t_end ? ldg_nc_v4(cptr) : make_uint4(0, 0, 0, 0); cptr += cstride; }   // step 1
-        advance(it3); advance(it3);                                               // prep() loads step 2 into cbA
-        bh_next = *reinterpret_cast<const float4*>(gbl); br_next = *reinterpret_cast<const float2*>(gbl + 4);
-        prep(cbA, 0, true);                                                       // leaves it1 = step 1, it3 = step 3
-    } else {
-        if (producer) service();                                                  // the first four pieces
-        stage_history(); stage_history(); stage_history();                        // steps 0, 1, 2
-    }
-    bar_sync_id(4, NCOMP);
-
-    uint32_t sb = 0, fph = 0, kp = 0, epar = 0, hph = 0;
-    float sel_row = 0.5f;
-    for (int t = t_begin; t < t_end; t++) {
-        {   // this warp's utterance in the softmax
-            const int b = tile * TU + warp;
-            sel_row = b < B ? p.sel[(size_t)t * B + b] : 0.5f;
-        }
-        if (chain) {
-            // ---------------- embedding (reference.cpp:42-57), this warp's 8 channels
-            if (tid == 0) TRACE(0, 1);
-            {
-                const int yc0 = ys[g], yc1 = ys[g + 8];
-                const uint32_t eo = sm + M::O_EPBUF + epar * (TU * EROW * 4);
-                const float2 a0 = unpack_h2(lds32(eo + (g * EROW + 4 * w + t4) * 4)), a1 = unpack_h2(lds32(eo + ((g + 8) * EROW + 4 * w + t4) * 4));
-                const float2 c0 = unpack_h2(lds32(sm + M::O_EMB + (yc0 * EROW + 4 * w + t4) * 4)), c1 = unpack_h2(lds32(sm + M::O_EMB + (yc1 * EROW + 4 * w + t4) * 4));
-                xres[0] = a0.x + c0.x; xres[1] = a0.y + c0.y; xres[2] = a1.x + c1.x; xres[3] = a1.y + c1.y;
-                if (p.tanhEmbed) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) xres[i] = wn::tanhf_fast(xres[i]);
-                }
-                const uint32_t x01 = pack_h2(xres[0], xres[1]), x23 = pack_h2(xres[2], xres[3]);
-                sts64(sm + M::O_XBUF + xchg, x01, x23);
-                stg_v2(gring_tile + lane16 + (size_t)((uint32_t)(it0.slot * L) * rstride) + jw * 512 + hw * 8, x01, x23);
-                const unsigned char* ep = static_cast<const unsigned char*>(p.embPrev);
-                const uint32_t en = sm + M::O_EPBUF + (epar ^ 1) * (TU * EROW * 4);
-                cp_async4(en + (g * EROW + 4 * w + t4) * 4, ep + (size_t)yc0 * 128 + (4 * w + t4) * 4);
-                cp_async4(en + ((g + 8) * EROW + 4 * w + t4) * 4, ep + (size_t)yc1 * 128 + (4 * w + t4) * 4);
-                cp_async_commit();
-            }
-            bar_compute();
-#pragma unroll
-            for (int j = 0; j < 4; j++) load_a(xa[j], sm + M::O_XBUF + j * 512 + lane16);
-            if (tid == 0) TRACE(0, 2);
-        }
-
-        for (int l = 0; l < L; l++) {
-            const uint32_t p1 = sm + M::O_RING1 + sb * C::SLOT1, p2 = sm + M::O_RING2 + sb * C::SLOT2;
-            const uint32_t f1 = s_full + sb * 8, f2 = s_full + 16 + sb * 8, e1 = s_empty + sb * 8, e2 = s_empty + 16 + sb * 8;
-            const uint32_t hb = sm + M::O_HBUF + kp * 2048;
-            if (chain) {
-                // ================================================== chain step
-                const float2 br = brn;
-                mbar_wait_a(f1, fph);
-                {
-                    const uint4 bt0 = lds128(p1 + o_t0), bg0 = lds128(p1 + o_g0), bt1 = lds128(p1 + o_t0 + 512), bg1 = lds128(p1 + o_g0 + 512);
-                    float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
-                    hmma(accp[0], xa[0], bt0.x, bt0.y); hmma(accp[1], xa[0], bg0.x, bg0.y); hmma(u0, xa[2], bt1.x, bt1.y); hmma(u1, xa[2], bg1.x, bg1.y);
-                    hmma(accp[0], xa[1], bt0.z, bt0.w); hmma(accp[1], xa[1], bg0.z, bg0.w); hmma(u0, xa[3], bt1.z, bt1.w); hmma(u1, xa[3], bg1.z, bg1.w);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
-                }
-                // the h tile of two steps ago has been read by the background warps once this step's [Wres | Wskip] piece has landed
-                mbar_wait_a(f2, fph);
-                {
-                    const __half2 half = __floats2half2_rn(0.5f, 0.5f);
-                    const __half2 tg0 = wn::tanh_h2(h2(pack_h2(accp[0][0], accp[0][1]))), tg1 = wn::tanh_h2(h2(pack_h2(accp[0][2], accp[0][3])));
-                    const __half2 sg0 = __hfma2(wn::tanh_h2(h2(pack_h2(0.5f * accp[1][0], 0.5f * accp[1][1]))), half, half);
-                    const __half2 sg1 = __hfma2(wn::tanh_h2(h2(pack_h2(0.5f * accp[1][2], 0.5f * accp[1][3]))), half, half);
-                    sts64(hb + xchg, u32(__hmul2(tg0, sg0)), u32(__hmul2(tg1, sg1)));
-                }
-                release(s_hrdy + 8 * kp);                              // h is on its way to the background warps
-                if (tid == 0) TRACE(0, 12);
-                if (kp == 0) prep(cbB, p1, false); else prep(cbA, p1, false);
-                release(e1);
-                bar_compute();
-                uint32_t ha[4][4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) load_a(ha[j], hb + j * 512 + lane16);
-                if (tid == 0) TRACE(0, 10);
-                float ra[4] = {0.f, 0.f, 0.f, 0.f}, rb[4] = {0.f, 0.f, 0.f, 0.f};
-                {
-                    const uint4 bw0 = lds128(p2 + o_res), bw1 = lds128(p2 + o_res + 512);
-                    hmma(ra, ha[0], bw0.x, bw0.y); hmma(rb, ha[2], bw1.x, bw1.y);
-                    hmma(ra, ha[1], bw0.z, bw0.w); hmma(rb, ha[3], bw1.z, bw1.w);
-                }
-                release(e2);
-                xres[0] = ((ra[0] + rb[0]) + br.x) + xres[0]; xres[1] = ((ra[1] + rb[1]) + br.y) + xres[1];
-                xres[2] = ((ra[2] + rb[2]) + br.x) + xres[2]; xres[3] = ((ra[3] + rb[3]) + br.y) + xres[3];
-                if (l + 1 < L) {
-                    const uint32_t x01 = pack_h2(xres[0], xres[1]), x23 = pack_h2(xres[2], xres[3]);
-                    sts64(sm + M::O_XBUF + xchg, x01, x23);
-                    stg_v2(gring_tile + lane16 + (size_t)((uint32_t)(it0.slot * L + l + 1) * rstride) + jw * 512 + hw * 8, x01, x23);
-                }
-                if (tid == 0) TRACE(0, 14);
-                if (DUMP) {
-                    if (v0) { p.xtOut[((size_t)l * B + b0) * R + cw] = xres[0]; p.xtOut[((size_t)l * B + b0) * R + cw + 1] = xres[1]; }
-                    if (v1) { p.xtOut[((size_t)l * B + b1) * R + cw] = xres[2]; p.xtOut[((size_t)l * B + b1) * R + cw + 1] = xres[3]; }
-                }
-                if (l + 1 < L) {
-                    bar_compute();
-#pragma unroll
-                    for (int j = 0; j < 4; j++) load_a(xa[j], sm + M::O_XBUF + j * 512 + lane16);
-                }
-                if (tid == 0) TRACE(0, 11);
-            } else {
-                // ================================================== background step
-                release(e1);                                            // the [Wcur | Wprev] piece belongs to the chain warps
-                if (producer) service();
-                if (w == 4 && lane < 8) {                               // pull the conditioning tile of 8 steps ahead towards L2
-                    const unsigned char* pf = cpf + (size_t)8 * cstride + lane * 512;
-                    if ((size_t)(pf - gcond_tile) < (size_t)t_end * L * cstride) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) prefetch_l2_line(pf + i * 128);
-                    }
-                }
-                cpf += cstride;
-                if (tid == 256) TRACE(1, 17);
-                wait_bar(s_hrdy + 8 * kp, hph);                         // h of this step is in hb
-                if (tid == 256) TRACE(1, 16);
-                hph ^= kp;                                              // each of the two barriers completes every second step
-                uint32_t ha[4][4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) load_a(ha[j], hb + j * 512 + lane16);
-                wait_bar(f2, fph);
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    uint4 bw[C::NSK];
-#pragma unroll
-                    for (int i = 0; i < C::NSK; i++) bw[i] = lds128(p2 + o_skip + (i * 2 + jp) * 512);
-#pragma unroll
-                    for (int i = 0; i < C::NSK; i++) hmma(sk[i], ha[2 * jp], bw[i].x, bw[i].y);
-#pragma unroll
-                    for (int i = 0; i < C::NSK; i++) hmma(sk[i], ha[2 * jp + 1], bw[i].z, bw[i].w);
-                }
-                release(e2);
-                if (tid == 256) TRACE(1, 15);
-                if (producer) service();
-                stage_history();                                        // the history tile of three steps ahead
-                if (DUMP) {
-                    const float* pre = gbias + im.b_skpre + (size_t)l * S;
-#pragma unroll
-                    for (int i = 0; i < C::NSK; i++) {
-                        const int c = 8 * (w * C::NSK + i) + 2 * t4;
-                        float o0 = sk[i][0] + pre[c], o1 = sk[i][1] + pre[c + 1], o2 = sk[i][2] + pre[c], o3 = sk[i][3] + pre[c + 1];
-                        if (l == L - 1) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
-                        if (v0) { p.skipOut[((size_t)l * B + b0) * S + c] = o0; p.skipOut[((size_t)l * B + b0) * S + c + 1] = o1; }
-                        if (v1) { p.skipOut[((size_t)l * B + b1) * S + c] = o2; p.skipOut[((size_t)l * B + b1) * S + c + 1] = o3; }
-                    }
-                }
-            }
-            fph ^= sb; sb ^= 1; kp ^= 1;
-        }
-
-        // ---------------- relu(skip + bias) -> Zs -> Za   (reference.cpp:93-104): all 16 warps, two n-tiles each
-        if (!chain) {
-#pragma unroll
-            for (int i = 0; i < C::NSK; i++) {
-                const int nt = w * C::NSK + i, c = 8 * nt + 2 * t4;
-                const float b0f = s_bout[c], b1f = s_bout[c + 1];
-                sts64(sm + M::O_OB0 + (nt >> 1) * 512 + lane16 + (nt & 1) * 8,
-                      pack_h2(fmaxf(sk[i][0] + b0f, 0.f), fmaxf(sk[i][1] + b1f, 0.f)), pack_h2(fmaxf(sk[i][2] + b0f, 0.f), fmaxf(sk[i][3] + b1f, 0.f)));
-                sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
-            }
-        }
-        bar_sync_id(4, NCOMP);
-        if (tid == 0) TRACE(0, 20);
-        float zz[2][4], zu[2][4];                                       // two n-tiles x two half-K chains
-        const int co = 16 * warp + 2 * t4;                              // first class of this thread inside the warp's 16
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            zz[i][0] = zz[i][2] = s_bout[S + co + 8 * i]; zz[i][1] = zz[i][3] = s_bout[S + co + 8 * i + 1];
-            zu[i][0] = zu[i][1] = zu[i][2] = zu[i][3] = 0.f;
-        }
-        auto out_gemm = [&](const int q, const int ojp, const uint32_t abuf, const int kp0) {
-            const uint32_t idx = sb ^ ((q >> 1) & 1), bo = ((q & 1) * 2 + idx) * 8;
-            const uint32_t st = ((q & 1) ? sm + M::O_RING2 + idx * C::SLOT2 : sm + M::O_RING1 + idx * C::SLOT1) + o_out * ojp + lane16;
-            wait_bar(s_full + bo, fph ^ (((sb + (q >> 1)) >> 1) & 1));
-            for (int jp = 0; jp < ojp; jp++) {
-                uint32_t a0[4], a1[4];
-                load_a(a0, abuf + ((kp0 + jp) * 2) * 512 + lane16);
-                load_a(a1, abuf + ((kp0 + jp) * 2 + 1) * 512 + lane16);
-                const uint4 bw0 = lds128(st + (0 * ojp + jp) * 512), bw1 = lds128(st + (1 * ojp + jp) * 512);
-                hmma(zz[0], a0, bw0.x, bw0.y); hmma(zz[1], a0, bw1.x, bw1.y);
-                hmma(zu[0], a1, bw0.z, bw0.w); hmma(zu[1], a1, bw1.z, bw1.w);
-            }
-            release(s_empty + bo);
-        };
-#pragma unroll
-        for (int q = 0; q < C::NQ_ZS; q++) out_gemm(q, C::OJP_ZS, sm + M::O_OB0, q * C::OJP_ZS);
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int c = co + 8 * i;
-            const float z0 = fmaxf(zz[i][0] + zu[i][0], 0.f), z1 = fmaxf(zz[i][1] + zu[i][1], 0.f), z2 = fmaxf(zz[i][2] + zu[i][2], 0.f), z3 = fmaxf(zz[i][3] + zu[i][3], 0.f);
-            sts64(sm + M::O_OB1 + warp * 512 + lane16 + i * 8, pack_h2(z0, z1), pack_h2(z2, z3));
-            if (DUMP) {
-                if (v0) { p.Zs[(size_t)b0 * A + c] = z0; p.Zs[(size_t)b0 * A + c + 1] = z1; }
-                if (v1) { p.Zs[(size_t)b1 * A + c] = z2; p.Zs[(size_t)b1 * A + c + 1] = z3; }
-            }
-            zz[i][0] = zz[i][2] = s_bout[S + A + c]; zz[i][1] = zz[i][3] = s_bout[S + A + c + 1];
-            zu[i][0] = zu[i][1] = zu[i][2] = zu[i][3] = 0.f;
-        }
-        bar_sync_id(4, NCOMP);
-        if (tid == 0) TRACE(0, 21);
-#pragma unroll
-        for (int q = 0; q < C::NQ_ZA; q++) out_gemm(C::NQ_ZS + q, C::OJP_ZA, sm + M::O_OB1, q * C::OJP_ZA);
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int c = co + 8 * i;
-            const float z0 = zz[i][0] + zu[i][0], z1 = zz[i][1] + zu[i][1], z2 = zz[i][2] + zu[i][2], z3 = zz[i][3] + zu[i][3];
-            sts64(sm + M::O_LBUF + (g * LROW + c) * 4, __float_as_uint(z0), __float_as_uint(z1));
-            sts64(sm + M::O_LBUF + ((g + 8) * LROW + c) * 4, __float_as_uint(z2), __float_as_uint(z3));
-            if (DUMP) {
-                if (v0) { p.Za[(size_t)b0 * A + c] = z0; p.Za[(size_t)b0 * A + c + 1] = z1; }
-                if (v1) { p.Za[(size_t)b1 * A + c] = z2; p.Za[(size_t)b1 * A + c + 1] = z3; }
-            }
-        }
-        bar_sync_id(4, NCOMP);
-        if (tid == 0) TRACE(0, 22);
-        if (producer) service();                                        // every output piece is consumed: the next sample's first pieces
-        // ---------------- softmax + categorical sample (matrix.cpp:167-183, reference.cpp:106-121): one utterance per warp,
-        // lane holds 8 consecutive classes
-        {
-            float e[8], m = 0.f;                                        // the reference starts the max at 0 (matrix.cpp:171)
-            const uint4 u0 = lds128(sm + M::O_LBUF + (warp * LROW + 8 * lane) * 4), u1 = lds128(sm + M::O_LBUF + (warp * LROW + 8 * lane + 4) * 4);
-            e[0] = __uint_as_float(u0.x); e[1] = __uint_as_float(u0.y); e[2] = __uint_as_float(u0.z); e[3] = __uint_as_float(u0.w);
-            e[4] = __uint_as_float(u1.x); e[5] = __uint_as_float(u1.y); e[6] = __uint_as_float(u1.z); e[7] = __uint_as_float(u1.w);
-#pragma unroll
-            for (int k = 0; k < 8; k++) m = fmaxf(m, e[k]);
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            const float ms = m * 1.4426950408889634f;
-            float run = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; k++) { run += wn::exp2f_fast(fmaf(e[k], 1.4426950408889634f, -ms)); e[k] = run; }
-            float incl = run;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const float a = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += a; }
-            const float total = __shfl_sync(0xffffffffu, incl, 31);
-            const float excl = incl - run;
-            const float target = sel_row * total;
-            int cntk = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) cntk += (target < excl + e[k]) ? 0 : 1;
-            const unsigned ball = __ballot_sync(0xffffffffu, target < incl);
-            const int lf = ball ? __ffs(ball) - 1 : 31;
-            const int ck = __shfl_sync(0xffffffffu, cntk, lf);
-            const int y = ball ? 8 * lf + (ck < 7 ? ck : 7) : A - 1;
-            const int b = tile * TU + warp;
-            if (DUMP && b < B) {
-                const float inv = 1.f / total;
-                float prevv = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; k++) { p.P[(size_t)b * A + 8 * lane + k] = (e[k] - prevv) * inv; prevv = e[k]; }
-            }
-            if (lane == 0) {
-                int fbk = y;
-                if (b < B) {
-                    p.yOut[(size_t)b * p.N + t] = y;
-                    if (p.forced) fbk = p.forced[(size_t)b * p.N + t];
-                } else fbk = 128;
-                ys[TU + warp] = ys[warp];
-                ys[warp] = fbk;
-            }
-        }
-        if (chain) cp_async_wait_all();                                 // the next sample's previous-index rows have landed
-        bar_sync_id(4, NCOMP);
-        if (tid == 0) TRACE(0, 23);
-        epar ^= 1;
-        if (++it0.slot == slots) it0.slot = 0;
-        it0.t++;
-    }
-    if (tid < TU && tile * TU + tid < B) { p.yCur[tile * TU + tid] = ys[tid]; p.yPrev[tile * TU + tid] = ys[TU + tid]; }
-#undef TRACE
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1272,6 +785,16 @@ cudaError_t wn_lat_cond_convert(void* dst, const float* src_dev, int first_sampl
     return cudaGetLastError();
 }
 
+cudaError_t wn_lat_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int L, int B, cudaStream_t stream)
+{
+    if (nsamples <= 0) return cudaSuccess;
+    const size_t total = (size_t)nsamples * L * B * 64;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    lat_cond_readback_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dst_dev, static_cast<const unsigned char*>(store), first_sample, nsamples, L, B, wn_lat_tiles(B));
+    return cudaGetLastError();
+}
+
 cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream)
 {
     const LatImage im = lat_image(p.S, p.L);
@@ -1282,52 +805,42 @@ cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream)
 }
 
 // p.B = utterances of this run; engine_B = batch size the conditioning store / history ring were laid out for
-// variant: 16 = role-specialised kernel (16 compute warps), 8 = the symmetric 8-warp kernel
 template <int S>
-static cudaError_t lat_launch_S(const WnParams& p, const unsigned char* im8, int grid, int ntiles_alloc, int variant, cudaStream_t stream, size_t* smem_out, int* block_out)
+static cudaError_t lat_launch_S(const WnParams& p, const unsigned char* im8, int grid, int ntiles_alloc, cudaStream_t stream, size_t* smem_out)
 {
-    const size_t smem = variant == 16 ? (size_t)Cfg2<S>::SMEM : (size_t)Cfg<S>::SMEM;
+    const size_t smem = Cfg<S>::SMEM;
     *smem_out = smem;
-    *block_out = variant == 16 ? NT2 : NT;
     cudaError_t e;
-#define LAT_GO(KERNEL, NTHREADS, PP)                                                                         \
-    do {                                                                                                     \
-        e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-        if (e != cudaSuccess) return e;                                                                      \
-        KERNEL<<<grid, NTHREADS, smem, stream>>>(PP, im8, ntiles_alloc);                                     \
-        e = cudaGetLastError();                                                                              \
-        if (e != cudaSuccess) return e;                                                                      \
+#define LAT_GO(DUMPV, TRCV, PP)                                                                                                    \
+    do {                                                                                                                           \
+        e = cudaFuncSetAttribute(wn_lat_kernel<S, DUMPV, TRCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        if (e != cudaSuccess) return e;                                                                                            \
+        wn_lat_kernel<S, DUMPV, TRCV><<<grid, NT, smem, stream>>>(PP, im8, ntiles_alloc);                                          \
+        e = cudaGetLastError();                                                                                                    \
+        if (e != cudaSuccess) return e;                                                                                            \
     } while (0)
     // a dumping launch = every sample but the last with the plain kernel, then the last one with the dumping variant
     // (a continuation is bit-identical to one launch: the whole state lives in global memory between launches)
     WnParams head = p, tail = p;
     if (p.dump) { head.count = p.count - 1; head.dump = 0; tail.init_sample = p.init_sample + p.count - 1; tail.count = 1; }
-    if (variant == 16) {
-        if (head.count > 0) {
-            if (p.trace) LAT_GO((wn_lat2_kernel<S, false, true>), NT2, head); else LAT_GO((wn_lat2_kernel<S, false, false>), NT2, head);
-        }
-        if (p.dump) LAT_GO((wn_lat2_kernel<S, true, false>), NT2, tail);
-    } else {
-        if (head.count > 0) {
-            if (p.trace) LAT_GO((wn_lat_kernel<S, false, true>), NT, head); else LAT_GO((wn_lat_kernel<S, false, false>), NT, head);
-        }
-        if (p.dump) LAT_GO((wn_lat_kernel<S, true, false>), NT, tail);
+    if (head.count > 0) {
+        if (p.trace) LAT_GO(false, true, head); else LAT_GO(false, false, head);
     }
+    if (p.dump) LAT_GO(true, false, tail);
 #undef LAT_GO
     return cudaSuccess;
 }
 
-cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, int variant, cudaStream_t stream, WnLaunchInfo* info)
+cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, cudaStream_t stream, WnLaunchInfo* info)
 {
     const int grid = wn_lat_tiles(p.B), ntiles_alloc = wn_lat_tiles(engine_B);
     const unsigned char* im8 = static_cast<const unsigned char*>(image);
     size_t smem = 0;
-    int block = 0;
     cudaError_t e;
-    if (p.S == 256) e = lat_launch_S<256>(p, im8, grid, ntiles_alloc, variant, stream, &smem, &block);
-    else if (p.S == 128) e = lat_launch_S<128>(p, im8, grid, ntiles_alloc, variant, stream, &smem, &block);
+    if (p.S == 256) e = lat_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);
+    else if (p.S == 128) e = lat_launch_S<128>(p, im8, grid, ntiles_alloc, stream, &smem);
     else return cudaErrorInvalidValue;
     if (e != cudaSuccess) return e;
-    if (info) { info->kernel = 18; info->grid = grid; info->block = block; info->smem_bytes = (int)smem; info->batch_per_cta = TU; info->cluster = 1; }
+    if (info) { info->kernel = 18; info->grid = grid; info->block = NT; info->smem_bytes = (int)smem; info->batch_per_cta = TU; info->cluster = 1; }
     return cudaGetLastError();
 }

@@ -93,6 +93,25 @@ __global__ void tc_cond_kernel(unsigned char* __restrict__ dst, const float* __r
     }
 }
 
+// inverse of tc_cond_kernel (debug / tests): conditioning store -> fp32 [n][L][B][2R]
+__global__ void tc_cond_readback_kernel(float* __restrict__ dst, const unsigned char* __restrict__ src, int first_sample, int nsamples, int L, int B, int TU)
+{
+    const size_t total = (size_t)nsamples * L * B * 16;
+    const size_t bpad = cond_bpad(B, TU);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 15);
+        const size_t rowi = i >> 4;
+        const int b = (int)(rowi % B);
+        const size_t sl = rowi / B;
+        const int tile = b / TU, r = b % TU, half = c >> 3, q = c & 7;
+        const size_t off = (((size_t)first_sample * L + sl) * bpad + (size_t)tile * TU) * 256 + (size_t)half * cond_rows(B, tile, TU) * 128 +
+                           (size_t)r * 128 + (size_t)((q ^ (r & 7)) << 4);
+        const __half2* v = reinterpret_cast<const __half2*>(src + off);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { dst[rowi * 128 + c * 8 + 2 * k] = __low2float(v[k]); dst[rowi * 128 + c * 8 + 2 * k + 1] = __high2float(v[k]); }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pack
 // blob (fp16, column-major matrices as uploaded) -> tiled / swizzled weight image + fp32 bias block
 __global__ void tc_pack_kernel(WnParams p, unsigned char* __restrict__ img, TcImage im)
@@ -1220,6 +1239,16 @@ cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     tc_cond_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<unsigned char*>(dst), src_dev, first_sample, nsamples, L, B, wn_tc_tile_utt(B, S));
+    return cudaGetLastError();
+}
+
+cudaError_t wn_tc_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream)
+{
+    if (nsamples <= 0) return cudaSuccess;
+    const size_t total = (size_t)nsamples * L * B * 16;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    tc_cond_readback_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dst_dev, static_cast<const unsigned char*>(store), first_sample, nsamples, L, B, wn_tc_tile_utt(B, S));
     return cudaGetLastError();
 }
 

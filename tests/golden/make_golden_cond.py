@@ -19,7 +19,8 @@ import wavenet as ref_wavenet  # noqa: E402  (the reference's module)
 out = {}
 #        name   C   T  window stride  L   R   B
 cases = [("a", 8, 2, 800, 200, 2, 32, 2),         # the reference's upsampling geometry (config.json: window 800, stride 200), 8 bands to keep the file small
-         ("b", 5, 7, 12, 4, 3, 4, 3)]             # odd small geometry: window = 3 strides
+         ("b", 5, 7, 12, 4, 3, 4, 3),             # odd small geometry: window = 3 strides
+         ("c", 6, 3, 40, 10, 4, 64, 19)]          # R = 64 (the tensor-core / latency kernels' tiled fp16 layouts), two 16-utterance tiles, ragged
 for name, C, T, window, stride, L, R, B in cases:
     torch.manual_seed(1234 + C)
     m = ref_wavenet.WaveNet(n_in_channels=256, n_layers=L, max_dilation=2, n_residual_channels=R, n_skip_channels=16,

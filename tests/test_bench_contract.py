@@ -22,6 +22,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     assert d["scaling"] == "weak" and d["data"] == "synthetic" and "workload" in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["metric"] == bench.metric_name() and "fp16" not in d["metric"]      # one metric string for both arms: precision lives in `dtype`
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     e2e = d["e2e"]

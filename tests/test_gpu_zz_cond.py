@@ -50,6 +50,34 @@ def test_generation_from_features_equals_generation_from_host_conditioning(dtype
     assert len(np.unique(ys[0])) > 2
 
 
+@pytest.mark.parametrize("kernel", ["fp32", "stream", "tc", "lat"])
+def test_device_conditioning_store_matches_reference_module(kernel, monkeypatch):
+    """The tensor the device producer leaves in the engine's conditioning store (read back through a debug getter, whatever the
+    kernel-native layout) against vectors from the reference's own WaveNet.get_cond_input (tests/golden/make_golden_cond.py):
+    fp32 within 1e-5 of the tensor scale, fp16 stores within 1e-3."""
+    import nv_wavenet_b200 as nw
+    from nv_wavenet_b200 import _lib
+    for k in ("NVWN_FP16_KERNEL", "NVWN_TC_TILE", "NVWN_TC_NODUP"):
+        monkeypatch.delenv(k, raising=False)
+    if kernel != "fp32":
+        monkeypatch.setenv("NVWN_FP16_KERNEL", kernel)
+    Cc, T, window, stride, L, R, B = [int(v) for v in GOLD["c_geometry"]]
+    N = T * stride + 5
+    first = 5
+    e = nw.NVWavenetInfer(L, 2, B, N, R=R, S=256, A=256, dtype=nw.FP32 if kernel == "fp32" else nw.FP16)
+    n = e.set_conditioning_from_features(GOLD["c_features"], GOLD["c_upsample_weight"], GOLD["c_upsample_bias"], GOLD["c_cond_weight"],
+                                         GOLD["c_cond_bias"], stride, first_sample=first)
+    assert n == T * stride
+    lib = _lib.lib()
+    lib.nvwn_debug_get_conditioning.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    got = np.full((n, L, B, 2 * R), np.nan, np.float32)
+    assert lib.nvwn_debug_get_conditioning(e._h, C.c_void_p(got.ctypes.data), first, n) == 0
+    want = GOLD["c_Lh"]
+    scale = np.abs(want).max()
+    tol = 1e-5 if kernel == "fp32" else 1e-3
+    assert np.isfinite(got).all() and np.abs(got - want).max() <= tol * scale, np.abs(got - want).max() / scale
+
+
 def test_out_of_range_is_rejected():
     import nv_wavenet_b200 as nw
     e = nw.NVWavenetInfer(2, 2, 2, 16, R=64, S=256, A=256, dtype=nw.FP32)
