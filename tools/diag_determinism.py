@@ -1,7 +1,7 @@
 """Run-to-run determinism of the fp16 kernels over a 2000-sample soak (C3 model): python tools/diag_determinism.py
-Round 2 finding: 128-row tensor-core tiles that are only partially filled ("nodup64", "nodup200") flip a sampled index about once
-per 1e5 utterance-samples; every other variant (32- / 64-utterance tiles full or ragged, full 128-row tiles, the latency kernel)
-is clean.  wn_tc_tile_utt() therefore never selects a ragged 128-row tile."""
+Round 2 finding: the 128-row tensor-core tiles (NVWN_TC_NODUP) flip a sampled index about once per 1e5 utterance-samples, most
+often when the tile is only partially filled; every other variant (32- / 64-utterance tiles full or ragged, the latency kernel) is
+clean.  wn_tc_tile_utt() therefore never selects 128-row tiles."""
 import os
 import sys
 
