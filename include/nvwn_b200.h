@@ -46,6 +46,13 @@ int nvwn_set_inputs(nvwn_engine* e, const float* Lh, const float* selectors);
 /* extension: selectors only / conditioning only (conditioning may be uploaded in chunks of whole samples) */
 int nvwn_set_selectors(nvwn_engine* e, const float* selectors);
 int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int num_samples, void* stream);
+/* extension: selectors drawn ON THE DEVICE, counter-based and stateless -- selector[i], i = sample *
+ * batch_size + b, is the first output of Philox-4x32-10 with counter (i, 0) and key `seed`, as (x >> 8) * 2^-24 in [0, 1)
+ * (the reference draws them on the host with libc rand(), pytorch/wavenet_infer.cu:92-93).  Asynchronous on `stream`. */
+int nvwn_set_selectors_random(nvwn_engine* e, unsigned long long seed, void* stream);
+/* host helper (needs no GPU): the selectors exactly as the reference wrapper draws them -- Matrix(batch, samples).randomize(0.5, 1.0)
+ * on the caller's libc rand() stream (pytorch/wavenet_infer.cu:92-93, matrix.cpp:38-56) -- into selectors[sample * batch_size + b]. */
+int nvwn_libc_selectors(float* selectors, int batch_size, int sample_count);
 /* Conditioning producer on the device.  Replaces, for inference, WaveNet.get_cond_input
  * (pytorch/wavenet.py:190-202: ConvTranspose1d(C, C, window, stride) upsampling trimmed by window - stride, then the
  * 1x1 cond_layers convolution C -> L*2R) and the permutes to [N][L][B][2R] (pytorch/nv_wavenet.py:48-49,181):

@@ -20,8 +20,8 @@
  *   - `implementation` 0..4 (AUTO, SINGLE_BLOCK, DUAL_BLOCK, PERSISTENT, MANYBLOCK) is accepted
  *     and ignored: one sm_100a kernel family replaces all four.
  *
- * The arithmetic of this entry point is bit-exact fp32.  Set the environment
- * variable NVWN_PRECISION=fp16 to route it through the fp16 tensor-core kernel instead.
+ * The arithmetic of this entry point is bit-exact fp32.  wavenet_infer_fp16 (below) takes the same arguments
+ * and runs the fp16 kernels (the reference builds a second library with T_data = half for that, README.md:24-25).
  */
 #ifndef WAVENET_INFER_H
 #define WAVENET_INFER_H
@@ -51,6 +51,11 @@ void wavenet_infer(int n_samples,                 /* sample_count */
                    float* conditioning,           /* cond_input  [n_samples][L][n_utterances][2R] */
                    int implementation,
                    int* samples_out);             /* samples     [n_utterances][n_samples] */
+
+/* Same arguments and semantics, fp16 arithmetic (weights, conditioning and GEMM inputs rounded to fp16, fp32 accumulation). */
+void wavenet_infer_fp16(int n_samples, int n_utterances, float* emb_prev, float* emb_cur, int n_layers, int max_dilation,
+                        float** w_prev, float** w_cur, float** b_gate, float** w_res, float** b_res, float** w_skip, float** b_skip,
+                        float* w_zs, float* w_za, int tanh_on_embedding, float* conditioning, int implementation, int* samples_out);
 
 /* channel counts of this build (pytorch/wavenet_infer.h:54-57) */
 int get_R(void);

@@ -31,6 +31,8 @@ SYMBOLS = {
     "nvwn_set_inputs": (C.c_int, [_vp, _vp, _vp]),
     "nvwn_set_selectors": (C.c_int, [_vp, _vp]),
     "nvwn_set_conditioning": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+    "nvwn_set_selectors_random": (C.c_int, [_vp, C.c_ulonglong, _vp]),
+    "nvwn_libc_selectors": (C.c_int, [_vp, C.c_int, C.c_int]),
     "nvwn_reset_history": (C.c_int, [_vp]),
     "nvwn_set_forced": (C.c_int, [_vp, _vp]),
     "nvwn_weight_blob": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_ulonglong)]),
@@ -50,6 +52,8 @@ SYMBOLS = {
     "nvwn_get_launch_info": (C.c_int, [_vp, C.POINTER(LaunchInfo)]),
     "nvwn_device_count": (C.c_int, []),
     "nvwn_set_device": (C.c_int, [C.c_int]),
+    "wavenet_infer_fp16": (None, [C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int] + [C.POINTER(_vp)] * 7
+                           + [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
     "wavenet_infer": (None, [C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int] + [C.POINTER(_vp)] * 7
                       + [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
     "get_R": (C.c_int, []),

@@ -23,23 +23,16 @@ void check(int rc, const char* what)
         exit(rc > 0 ? rc : 1);
     }
 }
-}  // namespace
 
-extern "C" {
-
-void wavenet_infer(int sample_count, int batch_size, float* embedding_prev, float* embedding_curr,
-                   int num_layers, int max_dilation,
-                   float** in_layer_weights_prev, float** in_layer_weights_curr, float** in_layer_biases,
-                   float** res_layer_weights, float** res_layer_biases,
-                   float** skip_layer_weights, float** skip_layer_biases,
-                   float* conv_out_weight, float* conv_end_weight, int use_embed_tanh,
-                   float* cond_input, int implementation, int* samples)
+void infer_impl(int dtype, int sample_count, int batch_size, float* embedding_prev, float* embedding_curr,
+                int num_layers, int max_dilation,
+                float** in_layer_weights_prev, float** in_layer_weights_curr, float** in_layer_biases,
+                float** res_layer_weights, float** res_layer_biases,
+                float** skip_layer_weights, float** skip_layer_biases,
+                float* conv_out_weight, float* conv_end_weight, int use_embed_tanh,
+                float* cond_input, int implementation, int* samples)
 {
     if (!samples) { fprintf(stderr, "wavenet_infer: samples must not be NULL\n"); abort(); }   // assert(samples), wavenet_infer.cu:142
-    int dtype = NVWN_FP32;
-    if (const char* env = getenv("NVWN_PRECISION")) {
-        if (!strcmp(env, "fp16")) dtype = NVWN_FP16;
-    }
     nvwn_engine* e = nullptr;
     check(nvwn_create(&e, dtype, R, S, A, num_layers, max_dilation, batch_size, sample_count,
                       (implementation >= 0 && implementation <= 4) ? NVWN_KERNEL_AUTO : implementation, use_embed_tanh),
@@ -54,19 +47,9 @@ void wavenet_infer(int sample_count, int batch_size, float* embedding_prev, floa
     std::vector<float> zero_bias(A, 0.f);
     check(nvwn_set_out_weights(e, conv_out_weight, zero_bias.data(), conv_end_weight, zero_bias.data()), "setOutWeights");
 
-    // Matrix outputSelectors(batch_size, sample_count); outputSelectors.randomize(0.5, 1.0)
-    // (wavenet_infer.cu:92-93, matrix.cpp:38-56): rows = batch visited outermost, two rand() per element,
-    // column-major storage => selectors[sample * batch_size + b].
+    // Matrix outputSelectors(batch_size, sample_count); outputSelectors.randomize(0.5, 1.0)  (wavenet_infer.cu:92-93): libc rand()
     std::vector<float> selectors((size_t)sample_count * batch_size);
-    for (int b = 0; b < batch_size; b++) {
-        for (int s = 0; s < sample_count; s++) {
-            (void)(rand() % 100);                                   // sparsity draw (sparsity = 0)
-            float r = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
-            r -= 0.5;
-            r = r * 1.0f + 0.5f;
-            selectors[(size_t)s * batch_size + b] = r;
-        }
-    }
+    check(nvwn_libc_selectors(selectors.data(), batch_size, sample_count), "selectors");
     check(nvwn_set_inputs(e, cond_input, selectors.data()), "setInputs");
     check(nvwn_run(e, sample_count, batch_size, samples, /*dumpActivations=*/1, nullptr), "run");
     cudaError_t ce = cudaDeviceSynchronize();
@@ -75,6 +58,30 @@ void wavenet_infer(int sample_count, int batch_size, float* embedding_prev, floa
         exit(ce);
     }
     nvwn_destroy(e);
+}
+}  // namespace
+
+extern "C" {
+
+void wavenet_infer(int sample_count, int batch_size, float* embedding_prev, float* embedding_curr, int num_layers, int max_dilation,
+                   float** in_layer_weights_prev, float** in_layer_weights_curr, float** in_layer_biases, float** res_layer_weights,
+                   float** res_layer_biases, float** skip_layer_weights, float** skip_layer_biases, float* conv_out_weight,
+                   float* conv_end_weight, int use_embed_tanh, float* cond_input, int implementation, int* samples)
+{
+    infer_impl(NVWN_FP32, sample_count, batch_size, embedding_prev, embedding_curr, num_layers, max_dilation, in_layer_weights_prev,
+               in_layer_weights_curr, in_layer_biases, res_layer_weights, res_layer_biases, skip_layer_weights, skip_layer_biases,
+               conv_out_weight, conv_end_weight, use_embed_tanh, cond_input, implementation, samples);
+}
+
+// same arguments, fp16 arithmetic (T_data = half build of the reference: README.md:24-25, a second .so there; a second symbol here)
+void wavenet_infer_fp16(int sample_count, int batch_size, float* embedding_prev, float* embedding_curr, int num_layers, int max_dilation,
+                        float** in_layer_weights_prev, float** in_layer_weights_curr, float** in_layer_biases, float** res_layer_weights,
+                        float** res_layer_biases, float** skip_layer_weights, float** skip_layer_biases, float* conv_out_weight,
+                        float* conv_end_weight, int use_embed_tanh, float* cond_input, int implementation, int* samples)
+{
+    infer_impl(NVWN_FP16, sample_count, batch_size, embedding_prev, embedding_curr, num_layers, max_dilation, in_layer_weights_prev,
+               in_layer_weights_curr, in_layer_biases, res_layer_weights, res_layer_biases, skip_layer_weights, skip_layer_biases,
+               conv_out_weight, conv_end_weight, use_embed_tanh, cond_input, implementation, samples);
 }
 
 int get_R(void) { return R; }

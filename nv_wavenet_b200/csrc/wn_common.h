@@ -44,4 +44,5 @@ bool wn_stream_supported(int R, int S, int A, bool fp16);
 // conversions (wn_convert.cu)
 cudaError_t wn_f32_to_f16(__half* dst, const float* src_dev, size_t n, cudaStream_t stream);
 cudaError_t wn_f16_to_f32(float* dst, const __half* src_dev, size_t n, cudaStream_t stream);
+cudaError_t wn_fill_selectors(float* dst, size_t n, unsigned long long seed, cudaStream_t stream);
 cudaError_t wn_fill_int(int* dst, int value, size_t n, cudaStream_t stream);

@@ -60,6 +60,35 @@ cudaError_t wn_f16_to_f32(float* dst, const __half* src_dev, size_t n, cudaStrea
     return cudaGetLastError();
 }
 
+// Counter-based selectors ("device-side Philox selectors"): element i of the [N][B] selector array is the
+// first 32-bit output of Philox-4x32-10 with counter (i_lo, i_hi, 0, 0) and key (seed_lo, seed_hi), mapped to [0, 1) with
+// 24 bits: (x >> 8) * 2^-24.  Stateless, order-independent, reproducible on the host (tests/test_gpu_zz_selectors.py).
+__host__ __device__ inline unsigned wn_philox_first(unsigned long long ctr, unsigned long long seed)
+{
+    unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0, c3 = 0;
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+__global__ void selectors_kernel(float* __restrict__ dst, size_t n, unsigned long long seed)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (float)(wn_philox_first(i, seed) >> 8) * (1.0f / 16777216.0f);
+}
+cudaError_t wn_fill_selectors(float* dst, size_t n, unsigned long long seed, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    selectors_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dst, n, seed);
+    return cudaGetLastError();
+}
+
 cudaError_t wn_fill_int(int* dst, int value, size_t n, cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;

@@ -16,7 +16,9 @@
 #include <string>
 #include <vector>
 
-cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image, cudaStream_t stream, WnLaunchInfo* info);   // wn_tc_kernel.cu
+cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image, int TU, bool fused, cudaStream_t stream, WnLaunchInfo* info);   // wn_tc_kernel.cu
+int wn_tc_tile_utt(int B, int S);
+bool wn_tc_fused_default();
 bool wn_tc_supported(int R, int S, int A, int L, int B);
 cudaError_t wn_cond_transpose_wu(float* WuT, const float* Wu, int C, int K, cudaStream_t stream);              // wn_cond_producer.cu
 cudaError_t wn_cond_produce(float* out, float* U, const float* feat, const float* WuT, const float* bu, const float* Wc, const float* bc,
@@ -27,9 +29,9 @@ cudaError_t wn_mulaw_decode(const int* yOut, int N, int offset, int size, int B,
                             short* out_s, cudaStream_t stream);                                                  // wn_convert.cu
 size_t wn_tc_image_bytes(int R, int S, int A, int L);
 cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream);
-size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B);
-size_t wn_tc_cond_bytes(int S, int L, int B, int N);
-cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream);
+size_t wn_tc_ring_bytes(int TU, int L, int maxDil, int B);
+size_t wn_tc_cond_bytes(int TU, int L, int B, int N);
+cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int TU, int L, int B, cudaStream_t stream);
 // latency-mode fp16 kernel (wn_lat_kernel.cu)
 bool wn_lat_supported(int R, int S, int A, int L);
 size_t wn_lat_image_bytes(int S, int L);
@@ -38,7 +40,7 @@ size_t wn_lat_cond_bytes(int L, int B, int N);
 cudaError_t wn_lat_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
 cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream);
 cudaError_t wn_lat_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
-cudaError_t wn_tc_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream);
+cudaError_t wn_tc_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int TU, int L, int B, cudaStream_t stream);
 cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, cudaStream_t stream, WnLaunchInfo* info);
 
 namespace {
@@ -92,6 +94,8 @@ struct nvwn_engine {
     void* tc_image = nullptr;                // tensor-core kernel's pre-tiled weight image
     bool tc_dirty = true;
     bool tc_mode = false;                    // decided once at creation: conditioning + history use the tiled layouts
+    int tc_tile = 64;                        // utterances per tensor-core tile and its schedule: resolved ONCE at creation (the
+    bool tc_fused = false;                   // conditioning store, the history ring and every launch depend on them)
     bool lat_mode = false;                   // decided once at creation: latency-mode kernel (fragment-ordered layouts); tc_image holds its weight image
 
     float* lut_f = nullptr;                  // mu-law decode tables (nvwn_get_audio): A floats, then 2 x A int16 (wrap / saturate)
@@ -239,8 +243,9 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     {
         const int k = decide_fp16_kernel(dtype, impl, R, S, A, num_layers, batch_size);
         e->tc_mode = k == 1; e->lat_mode = k == 2;
+        if (e->tc_mode) { e->tc_tile = wn_tc_tile_utt(batch_size, S); e->tc_fused = wn_tc_fused_default() || e->tc_tile == 32; }
     }
-    ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(S, num_layers, batch_size, num_samples)
+    ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(e->tc_tile, num_layers, batch_size, num_samples)
                  : e->lat_mode ? wn_lat_cond_bytes(num_layers, batch_size, num_samples) : Nz * L * Bz * 2 * R * td);
     ALLOC(e->sel, Nz * Bz * sizeof(float));
     ALLOC(e->forced, Nz * Bz * sizeof(int));
@@ -249,7 +254,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     ALLOC(e->yOut, Nz * Bz * sizeof(int));
     size_t ring_bytes = (size_t)(max_dilation + 1) * L * Bz * R * td;
     if (e->tc_mode) {
-        const size_t tcb = wn_tc_ring_bytes(S, num_layers, max_dilation, batch_size);     // tiled history layout of the tensor-core kernel
+        const size_t tcb = wn_tc_ring_bytes(e->tc_tile, num_layers, max_dilation, batch_size);     // tiled history layout of the tensor-core kernel
         if (tcb > ring_bytes) ring_bytes = tcb;
     }
     if (e->lat_mode) ring_bytes = wn_lat_ring_bytes(num_layers, max_dilation, batch_size);
@@ -392,6 +397,30 @@ int nvwn_set_selectors(nvwn_engine* e, const float* selectors)
     return 0;
 }
 
+int nvwn_libc_selectors(float* selectors, int batch_size, int sample_count)
+{
+    if (!selectors || batch_size < 1 || sample_count < 1) return fail(NVWN_EINVAL, "nvwn_libc_selectors: bad argument");
+    // Matrix outputSelectors(batch_size, sample_count); outputSelectors.randomize(0.5, 1.0)  (pytorch/wavenet_infer.cu:92-93,
+    // matrix.cpp:38-56): rows = batch visited outermost, two rand() per element, column-major storage
+    for (int b = 0; b < batch_size; b++) {
+        for (int s = 0; s < sample_count; s++) {
+            (void)(rand() % 100);                                   // sparsity draw (sparsity = 0)
+            float r = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+            r -= 0.5;
+            r = r * 1.0f + 0.5f;
+            selectors[(size_t)s * batch_size + b] = r;
+        }
+    }
+    return 0;
+}
+
+int nvwn_set_selectors_random(nvwn_engine* e, unsigned long long seed, void* stream)
+{
+    if (!e) return fail(NVWN_EINVAL, "nvwn_set_selectors_random: NULL engine");
+    CK(wn_fill_selectors(e->sel, (size_t)e->N * e->B, seed, (cudaStream_t)stream));
+    return 0;
+}
+
 int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int num_samples, void* stream)
 {
     if (!e || !Lh) return fail(NVWN_EINVAL, "nvwn_set_conditioning: NULL argument");
@@ -404,7 +433,7 @@ int nvwn_set_conditioning(nvwn_engine* e, const float* Lh, int first_sample, int
     cudaStream_t st = (cudaStream_t)stream;
     auto convert = [&](const float* src_dev, int first, int n) {
         return e->lat_mode ? wn_lat_cond_convert(e->Lh, src_dev, first, n, e->L, e->B, st)
-                           : wn_tc_cond_convert(e->Lh, src_dev, first, n, e->S, e->L, e->B, st);
+                           : wn_tc_cond_convert(e->Lh, src_dev, first, n, e->tc_tile, e->L, e->B, st);
     };
     if (is_device_ptr(Lh)) {
         CK(convert(Lh, first_sample, num_samples));
@@ -482,7 +511,7 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
                 CK(wn_tc_pack(e->tc_image, p, stream));
                 e->tc_dirty = false;
             }
-            CK(wn_launch_tc(p, e->tc_image, stream, &e->last));
+            CK(wn_launch_tc(p, e->tc_image, e->tc_tile, e->tc_fused, stream, &e->last));
         } else {
             CK(wn_launch_stream(p, e->dtype == NVWN_FP16, stream, &e->last));
         }
@@ -595,7 +624,7 @@ int nvwn_debug_get_conditioning(nvwn_engine* e, float* out, int first_sample, in
     CK(cudaMalloc((void**)&tmp, n * sizeof(float)));
     cudaError_t ce;
     if (e->lat_mode) ce = wn_lat_cond_readback(tmp, e->Lh, first_sample, num_samples, e->L, e->B, 0);
-    else if (e->tc_mode) ce = wn_tc_cond_readback(tmp, e->Lh, first_sample, num_samples, e->S, e->L, e->B, 0);
+    else if (e->tc_mode) ce = wn_tc_cond_readback(tmp, e->Lh, first_sample, num_samples, e->tc_tile, e->L, e->B, 0);
     else if (e->dtype == NVWN_FP16) ce = wn_f16_to_f32(tmp, static_cast<const __half*>(e->Lh) + (size_t)first_sample * per, n, 0);
     else ce = cudaMemcpyAsync(tmp, static_cast<const float*>(e->Lh) + (size_t)first_sample * per, n * sizeof(float), cudaMemcpyDeviceToDevice, 0);
     if (ce == cudaSuccess) ce = cudaMemcpy(out, tmp, n * sizeof(float), cudaMemcpyDefault);

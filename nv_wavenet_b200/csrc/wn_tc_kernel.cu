@@ -1220,39 +1220,45 @@ int wn_tc_tile_utt(int B, int S)
 {
     if (getenv("NVWN_TC_NODUP")) return 128;
     if (const char* v = getenv("NVWN_TC_TILE")) { const int t = atoi(v); if (t == 128 || t == 64 || (t == 32 && S == 256)) return t; }
-    if (S == 256 && B <= 32 * 64) return 32;
-    // 128-row tiles (two threads per utterance) are NOT selected automatically any more: the round-2 soak test
-    // (tests/test_gpu_parity.py::test_fp16_soak_determinism_and_chunking, tools/diag_determinism.py) shows a rare run-to-run
-    // flip of a sampled index with them (about one per 1e5 utterance-samples; 32- / 64-utterance tiles, full or ragged, are
-    // clean over the same soak).  Open defect of that variant; batches beyond one wave of 64-utterance tiles run in several waves.
+    // Round 2: the soak test (tests/test_gpu_parity.py::test_fp16_soak_determinism_and_chunking, tools/diag_determinism.py) shows
+    // rare run-to-run flips of a sampled index (about one per 1e5 utterance-samples) with the FUSED schedule (32- / 64-utterance
+    // tiles) and with the 128-row tiles; the unfused schedule on 64-utterance tiles is clean over the same soak.  Those variants
+    // stay reachable through NVWN_TC_TILE / NVWN_TC_NODUP / NVWN_TC_FUSED for investigation but are never selected automatically
+    // (the latency-mode kernel, wn_lat_kernel.cu, serves the batches they were meant for).
     return 64;
 }
 
-size_t wn_tc_ring_bytes(int S, int L, int maxDil, int B)
+// schedule of an engine, resolved once at creation: "0" / "1" in NVWN_TC_FUSED force one (tests); see wn_tc_tile_utt() for the default
+bool wn_tc_fused_default()
 {
-    const int TU = wn_tc_tile_utt(B, S);
+    const char* fv = getenv("NVWN_TC_FUSED");
+    return fv ? fv[0] != '0' : false;
+}
+
+size_t wn_tc_ring_bytes(int TU, int L, int maxDil, int B)
+{
     return (size_t)(maxDil + 1) * L * ((B + TU - 1) / TU) * TILE;
 }
 
-size_t wn_tc_cond_bytes(int S, int L, int B, int N) { return (size_t)N * L * cond_bpad(B, wn_tc_tile_utt(B, S)) * 256; }
+size_t wn_tc_cond_bytes(int TU, int L, int B, int N) { return (size_t)N * L * cond_bpad(B, TU) * 256; }
 
-cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream)
+cudaError_t wn_tc_cond_convert(void* dst, const float* src_dev, int first_sample, int nsamples, int TU, int L, int B, cudaStream_t stream)
 {
     if (nsamples <= 0) return cudaSuccess;
     const size_t total = (size_t)nsamples * L * B * 16;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    tc_cond_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<unsigned char*>(dst), src_dev, first_sample, nsamples, L, B, wn_tc_tile_utt(B, S));
+    tc_cond_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<unsigned char*>(dst), src_dev, first_sample, nsamples, L, B, TU);
     return cudaGetLastError();
 }
 
-cudaError_t wn_tc_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int S, int L, int B, cudaStream_t stream)
+cudaError_t wn_tc_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int TU, int L, int B, cudaStream_t stream)
 {
     if (nsamples <= 0) return cudaSuccess;
     const size_t total = (size_t)nsamples * L * B * 16;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    tc_cond_readback_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dst_dev, static_cast<const unsigned char*>(store), first_sample, nsamples, L, B, wn_tc_tile_utt(B, S));
+    tc_cond_readback_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dst_dev, static_cast<const unsigned char*>(store), first_sample, nsamples, L, B, TU);
     return cudaGetLastError();
 }
 
@@ -1265,12 +1271,11 @@ cudaError_t wn_tc_pack(void* image, const WnParams& p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t stream, WnLaunchInfo* info)
+cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, int TU, bool fused, cudaStream_t stream, WnLaunchInfo* info)
 {
     const int nstage = pick_nstage(p.S, p.L);
     if (nstage < 3) return cudaErrorInvalidValue;
     const size_t smem = tc_smem_bytes(p.S, p.L, nstage);
-    const int TU = wn_tc_tile_utt(p.B, p.S);
     const int grid = (p.B + TU - 1) / TU;
     cudaError_t e = cudaErrorInvalidValue;
     const int cp = 128 / TU;                                    // row copies per utterance: 2 cp threads work for each
@@ -1278,9 +1283,6 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t 
     // Fused schedule (one MMA<->epilogue round trip per layer, +1 weight chunk per layer) while the launch is latency-bound;
     // with (nearly) every SM streaming the weights from L2 the extra chunk costs more than the round trip saves
     // (measured, 64-utterance tiles: 2048 utt. 50.9M vs 44.5M samples/s fused; 9472 utt. 175.6M fused vs 196.4M unfused).
-    const char* fv = getenv("NVWN_TC_FUSED");                   // "0" / "1" force a schedule (tests)
-    const int fused_env = fv ? (fv[0] == '0' ? 0 : 1) : -1;
-    const bool fused = fused_env >= 0 ? fused_env == 1 : !(TU == 64 && grid > 96);
 #define WN_TC_LAUNCH(SV, DV, FV)                                                                                     \
     do {                                                                                                             \
         e = cudaFuncSetAttribute(wn_tc_kernel<SV, DV, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
@@ -1289,7 +1291,7 @@ cudaError_t wn_launch_tc(const WnParams& p, const void* tc_image_, cudaStream_t 
     } while (0)
 #define WN_TC_LAUNCH2(SV, DV) do { if (fused) WN_TC_LAUNCH(SV, DV, true); else WN_TC_LAUNCH(SV, DV, false); } while (0)
     if (p.S == 256) {
-        if (cp == 4) WN_TC_LAUNCH(256, 4, true);                // 32-utterance tiles exist for the fused schedule only
+        if (cp == 4) WN_TC_LAUNCH(256, 4, true);                // 32-utterance tiles exist for the fused schedule only (NVWN_TC_TILE=32)
         else if (cp == 2) WN_TC_LAUNCH2(256, 2);
         else WN_TC_LAUNCH2(256, 1);
     } else {

@@ -94,6 +94,10 @@ class NVWavenetInfer:
         s, k = _ptr(output_selectors, np.float32)
         check(self._l.nvwn_set_selectors(self._h, s), "setSelectors")
 
+    def set_selectors_random(self, seed, stream=None):
+        """Selectors drawn on the device: counter-based (Philox-4x32-10, key = seed), see include/nvwn_b200.h."""
+        check(self._l.nvwn_set_selectors_random(self._h, C.c_ulonglong(int(seed) & (2 ** 64 - 1)), _stream(stream)), "setSelectorsRandom")
+
     def set_conditioning(self, Lh, first_sample, num_samples, stream=None):
         a, k = _ptr(Lh, np.float32)
         check(self._l.nvwn_set_conditioning(self._h, a, first_sample, num_samples, _stream(stream)), "setConditioning")

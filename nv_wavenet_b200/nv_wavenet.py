@@ -1,9 +1,14 @@
 """PyTorch-facing binding with the surface of the reference's `pytorch/nv_wavenet.py` -- class `NVWaveNet`, the `Impl`
-constants and `column_major` -- implemented over the kept C-ABI `wavenet_infer` through ctypes (the reference's
+constants and `column_major` -- implemented over the handle C-ABI (include/nvwn_b200.h) through ctypes (the reference's
 THC-era pybind wrapper, `pytorch/wavenet_infer_wrapper.cpp`, no longer builds against torch >= 2).
 
     wavenet = NVWaveNet(**model.export_weights())
     samples = wavenet.infer(cond_input, Impl.PERSISTENT)      # int32 CUDA tensor [batch, samples]
+
+Unlike the reference wrapper (pytorch/wavenet_infer.cu:87-145 builds the whole nvWavenetInfer object, uploads every weight and
+frees it again on EVERY call) the object keeps a persistent engine per (batch, samples, precision): weights are uploaded once,
+infer() only sets the inputs.  Selectors: `seed=None` draws them like the reference (libc rand(), replayable with srand());
+an integer seed draws them on the device (counter-based Philox, include/nvwn_b200.h).
 
 Constructor arguments, accepted shapes, the appended unused residual layer and the memory layouts handed to the
 kernel are those of pytorch/nv_wavenet.py:55-196; the code is organised around one table of expected shapes.
@@ -89,20 +94,45 @@ class NVWaveNet:
             self.layers.append((column_major(w[:, :, 0]), column_major(w[:, :, 1]), dilate_biases[l],
                                 column_major(res_weights[l]), res_biases[l], column_major(skip_weights[l]), skip_biases[l]))
         self.num_layers = n
+        self._engines = {}                               # (batch, samples, fp16) -> persistent NVWavenetInfer
+        self.engines_created = 0
 
-    def infer(self, cond_input, implementation):
-        """cond_input: channels x batch x num_layers x samples (pytorch/nv_wavenet.py:172-196); returns int32 [batch][samples]."""
+    def _engine(self, batch_size, sample_count, fp16):
+        """The persistent engine for this problem size (created and loaded on first use)."""
+        from .infer import NVWavenetInfer
+        key = (batch_size, sample_count, bool(fp16))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = NVWavenetInfer(self.num_layers, self.max_dilation, batch_size, sample_count, 0, bool(self.use_embed_tanh),
+                                 R=self.R, S=self.S, A=self.A, dtype=_lib.FP16 if fp16 else _lib.FP32)
+            f32 = lambda t: t.float().contiguous()
+            eng.set_embeddings(f32(self.embedding_prev), f32(self.embedding_curr))
+            for l, layer in enumerate(self.layers):
+                eng.set_layer_weights(l, *[f32(t) for t in layer])
+            zero = torch.zeros(self.A, dtype=torch.float32)                 # "We didn't use biases on our outputs" (wavenet_infer.cu:75-82)
+            eng.set_out_weights(f32(self.conv_out), zero, f32(self.conv_end), zero)
+            self._engines[key] = eng
+            self.engines_created += 1
+        return eng
+
+    def infer(self, cond_input, implementation, seed=None, fp16=False):
+        """cond_input: channels x batch x num_layers x samples (pytorch/nv_wavenet.py:172-196); returns int32 [batch][samples].
+        `implementation` (Impl.*) is accepted for compatibility: one kernel family serves all of them."""
         if (cond_input.size(0), cond_input.size(2)) != (2 * self.R, self.num_layers):
             raise AssertionError(f"Inputs are channels x batch x num_layers x samples; got {tuple(cond_input.size())}")
         batch_size, sample_count = cond_input.size(1), cond_input.size(3)
+        eng = self._engine(batch_size, sample_count, fp16)
         lh = column_major(cond_input).float()                       # [samples][layers][batch][2R]
+        eng.reset_history()
+        eng.set_conditioning(lh, 0, sample_count)
+        if seed is None:                                            # the reference's host draw, on the caller's rand() stream
+            import numpy as np
+            sel = np.empty(sample_count * batch_size, np.float32)
+            _lib.check(self._lib.nvwn_libc_selectors(C.c_void_p(sel.ctypes.data), batch_size, sample_count), "selectors")
+            eng.set_selectors(sel)
+        else:
+            eng.set_selectors_random(seed)
         samples = torch.empty((batch_size, sample_count), dtype=torch.int32, device="cuda")
-        f32 = lambda t: t.float().contiguous()
-        per_layer = [[f32(t) for t in layer] for layer in self.layers]   # keeps the buffers alive across the call
-        column = lambda k: (C.c_void_p * self.num_layers)(*[layer[k].data_ptr() for layer in per_layer])
-        emb_prev, emb_cur, conv_out, conv_end = f32(self.embedding_prev), f32(self.embedding_curr), f32(self.conv_out), f32(self.conv_end)
-        self._lib.wavenet_infer(sample_count, batch_size, emb_prev.data_ptr(), emb_cur.data_ptr(), self.num_layers, self.max_dilation,
-                                column(0), column(1), column(2), column(3), column(4), column(5), column(6),
-                                conv_out.data_ptr(), conv_end.data_ptr(), int(bool(self.use_embed_tanh)),
-                                lh.data_ptr(), implementation, samples.data_ptr())
+        eng.run(sample_count, batch_size, samples, dump_activations=False)
+        torch.cuda.synchronize()
         return samples

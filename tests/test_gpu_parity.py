@@ -159,7 +159,7 @@ def _logit_check(za_o, za_g, rel=1e-2, mean_rel=None):
         assert (err / scale).mean() <= mean_rel, f"mean err / scale {(err / scale).mean()}"
 
 
-FP16_KERNELS = ["stream", "lat", "tc", "tc_tile64", "tc_tile64_unfused", "tc_nodup"]
+FP16_KERNELS = ["stream", "lat", "tc", "tc_tile32_fused", "tc_tile64_fused", "tc_nodup"]
 
 
 def _select_fp16_kernel(kernel, monkeypatch):
@@ -170,14 +170,14 @@ def _select_fp16_kernel(kernel, monkeypatch):
         monkeypatch.setenv("NVWN_FP16_KERNEL", "stream")
     elif kernel == "lat":                          # latency-mode kernel (mma.sync, 16-utterance tiles): what AUTO picks up to 2368 utterances
         monkeypatch.setenv("NVWN_FP16_KERNEL", "lat")
-    else:                                          # tensor-core (tcgen05) kernel: 32-utterance tiles unless told otherwise
+    else:                                          # tensor-core (tcgen05) kernel; "tc" = the auto-selected 64-utterance tiles, unfused schedule
         monkeypatch.setenv("NVWN_FP16_KERNEL", "tc")
-        if kernel == "tc_nodup":                   # 128-utterance tiles, two threads per utterance (the large-batch variant)
+        if kernel == "tc_nodup":                   # 128-utterance tiles, two threads per utterance (debug variant, see wn_tc_tile_utt)
             monkeypatch.setenv("NVWN_TC_NODUP", "1")
-        if kernel.startswith("tc_tile64"):         # 64-utterance tiles, four threads per utterance
-            monkeypatch.setenv("NVWN_TC_TILE", "64")
-        if kernel == "tc_tile64_unfused":          # the two-round-trip schedule that launches filling the GPU use
-            monkeypatch.setenv("NVWN_TC_FUSED", "0")
+        if kernel == "tc_tile32_fused":            # 32-utterance tiles exist for the fused schedule only (debug variant)
+            monkeypatch.setenv("NVWN_TC_TILE", "32")
+        if kernel == "tc_tile64_fused":            # fused schedule on 64-utterance tiles (debug variant)
+            monkeypatch.setenv("NVWN_TC_TILE", "64"); monkeypatch.setenv("NVWN_TC_FUSED", "1")
 
 
 def _check_sampled_index(p, sel, y):
@@ -201,7 +201,7 @@ def _check_sampled_index(p, sel, y):
 ])
 def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
     R, S, A, L, B, N, md = shape
-    if kernel in ("stream", "tc_tile64_unfused") and B > 64:
+    if kernel in ("stream", "tc_tile64_fused") and B > 64:
         pytest.skip("covered by the smaller shapes")
     _select_fp16_kernel(kernel, monkeypatch)
     w = refgen.lively_inputs(21 + B, R, S, A, L, B, N)
@@ -238,7 +238,7 @@ def _run_range(e, init, count, N, B, y=None):
     e._samples_per_chunk = 0
 
 
-@pytest.mark.parametrize("kernel", ["lat", "tc", "tc_tile64", "tc_tile64_unfused"])      # not the 128-row tiles: known rare flip, never auto-selected
+@pytest.mark.parametrize("kernel", ["lat", "tc"])      # "tc" = what AUTO selects above the latency kernel's range: 64-utterance tiles, unfused schedule
 def test_fp16_soak_determinism_and_chunking(kernel, monkeypatch):
     """The fp16 kernels at the C3 shape (L20 R64 S256 A256, maxDil 512, 64 utterances) over 2000 samples -- several turns of the
     513-slot history ring and of the dilation cycle: run twice -> identical yOut; run_chunks(97) and three unequal
@@ -262,7 +262,7 @@ def test_fp16_soak_determinism_and_chunking(kernel, monkeypatch):
     assert np.array_equal(y1, y4), "three unequal run_partial pieces != one launch"
 
 
-@pytest.mark.parametrize("kernel", ["lat", "tc", "tc_tile64_unfused"])
+@pytest.mark.parametrize("kernel", ["lat", "tc"])
 def test_fp16_logits_after_ring_wrap(kernel, monkeypatch):
     """Teacher-forced logits at step N-1 = 599 > maxDil + 1 = 513 (real ring wrap, every dilation live) against the oracle."""
     R, S, A, L, B, N, md = 64, 256, 256, 20, 16, 600, 512
