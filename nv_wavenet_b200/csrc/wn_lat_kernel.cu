@@ -63,12 +63,12 @@ struct Cfg {
     static constexpr uint32_t O_RING2 = 2 * SLOT1;                   // 2 x SLOT2
     static constexpr uint32_t O_EMB = O_RING2 + 2 * SLOT2;
     static constexpr uint32_t O_BOUT = O_EMB + A * EROW * 4;         // fp32: Bskip total [S], Bzs [A], Bza [A]
-    static constexpr uint32_t O_XBUF = O_BOUT + (S + 2 * A) * 4;
-    static constexpr uint32_t O_HBUF = O_XBUF + 2048;
-    static constexpr uint32_t O_EPBUF = O_HBUF + 2048;
-    static constexpr uint32_t O_OB0 = O_EPBUF + 2 * TU * EROW * 4;          // two [16 rows][33 words] buffers (sample parity)
+    static constexpr uint32_t O_EPBUF = O_BOUT + (S + 2 * A) * 4;           // two [16 rows][33 words] buffers (sample parity)
+    static constexpr uint32_t O_PST = O_EPBUF + 2 * TU * EROW * 4;          // 3 x 2 KB: staged history tiles x[t-d] (A-fragment order)
+    static constexpr uint32_t O_OB0 = O_PST + 3 * 2048;
     static constexpr uint32_t O_OB1 = O_OB0 + (S / 16) * 512;
-    static constexpr uint32_t O_LBUF = O_OB1 + (A / 16) * 512;
+    static constexpr uint32_t O_LBUF = O_OB1 + (A / 16) * 512;              // transposed logits; its first 4 KB double as ...
+    static constexpr uint32_t O_XBUF = O_LBUF, O_HBUF = O_LBUF + 2048;      // ... the x and h exchange tiles (dead while the logits live)
     static constexpr uint32_t O_DIL = O_LBUF + TU * LROW * 4;
     static constexpr uint32_t O_YS = O_DIL + MAXL * 4;
     static constexpr uint32_t O_BAR = O_YS + 2 * TU * 4;
@@ -134,6 +134,12 @@ __device__ __forceinline__ uint4 ldg_cg_v4(const void* p)
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
     return r;
 }
+// predicated load into an existing register quad: no select on the loaded value, so nothing waits for the load here
+__device__ __forceinline__ void ldg_nc_v4_if(uint4& d, const void* p, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+r"(d.x), "+r"(d.y), "+r"(d.z), "+r"(d.w) : "l"(p), "r"((uint32_t)pred) : "memory");
+}
 __device__ __forceinline__ void stg_v2(void* p, uint32_t a, uint32_t b) { asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory"); }
 __device__ __forceinline__ void stg_v4(void* p, uint4 v) { asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
@@ -147,6 +153,9 @@ __device__ __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<ui
 __device__ __forceinline__ __half2 h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
 
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+// the mbarrier receives one arrival once every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -329,7 +338,7 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
     const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
 
     // mbarriers of the weight ring: piece n lives in slot (n >> 1) & 1 of slot type n & 1; one full / empty pair per slot
-    const uint32_t s_full = sm + C::O_BAR, s_empty = s_full + 32;
+    const uint32_t s_full = sm + C::O_BAR, s_empty = s_full + 32, s_pfull = s_full + 64;       // [4], [4], [3]
     int* dil = reinterpret_cast<int*>(smem_raw + C::O_DIL);
     int* ys = reinterpret_cast<int*>(smem_raw + C::O_YS);      // [TU] current index, [TU] previous index
     float* s_bout = reinterpret_cast<float*>(smem_raw + C::O_BOUT);
@@ -344,6 +353,7 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
 
     if (tid == 0) {
         for (int i = 0; i < 4; i++) { mbar_init_a(s_full + 8 * i, 1); mbar_init_a(s_empty + 8 * i, NCW); }
+        for (int i = 0; i < 3; i++) mbar_init_a(s_pfull + 8 * i, 128);
         fence_mbar_init();
         int d = 1;                                     // dilation of layer l (nv_wavenet.cuh:99-111): 1,2,4..maxDil,1,2,...
         for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; }
@@ -408,30 +418,37 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
         const uint32_t o_out = (uint32_t)(4 * w) * 512;                                                         // output pieces: x OJP, + lane16
 
         auto advance = [&](StepIt& it) { if (++it.l == L) { it.l = 0; it.t++; if (++it.slot == slots) it.slot = 0; } };
-        // dilated history x_l[t - d] of step `it` -> A fragments (zero before the start of the utterance, nv_wavenet.cuh:106)
-        auto ldP = [&](uint32_t (&x)[4][4], const StepIt& it) {
-            const int d = dil[it.l];
-            if (it.t >= t_end || it.t < d) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0; }
-                return;
-            }
-            int sl = it.slot - d; if (sl < 0) sl += slots;
-            const unsigned char* src = gring + (size_t)((uint32_t)(sl * L + it.l) * rstride);
-#pragma unroll
-            for (int j = 0; j < 4; j++) { const uint4 v = ldg_cg_v4(src + j * 512); x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w; }
-        };
-        const unsigned char* cptr;                     // conditioning of step it3 (steps are consecutive in memory)
-        auto ldC = [&](const StepIt& it) -> uint4 {
-            const unsigned char* src = cptr;
-            cptr += cstride;
-            if (it.t >= t_end) return make_uint4(0, 0, 0, 0);
-            return ldg_nc_v4(src);
-        };
         auto release = [&](uint32_t bar) { __syncwarp(); if (lane == 0) mbar_arrive_a(bar); };
+        // Every mbarrier wait costs ~90 cycles even when the phase completed long ago (TRYWAIT latency).  The barriers of the coming
+        // step are therefore looked at once, at the end of the running step (measured: 40.1 kHz at C3 B=64 against 38.4 kHz with
+        // plain waits at the point of use, and 35.9 kHz with blocking waits moved behind the preceding HMMA batches).
+        auto probe = [&](uint32_t bar, uint32_t parity) -> bool { return mbar_try_a(bar, parity); };
+        auto ensure = [&](bool ok, uint32_t bar, uint32_t parity) { if (!ok) mbar_wait_a(bar, parity); };
 
-        uint32_t xa[4][4], pbA[4][4], pbB[4][4];
-        uint4 cbA, cbB;
+        // dilated history x_l[t - d] (zero before the start of the utterance, nv_wavenet.cuh:106) of the step `itp`: staged three
+        // steps ahead into a 3-slot shared-memory ring by warps 0-3 (128 threads x 16 B, cp.async; completion on an mbarrier)
+        StepIt itp{t_begin, 0, t_begin % slots};
+        uint32_t pcnt = 0;                             // tiles staged so far (slot = pcnt % 3)
+        auto stage_history = [&]() {
+            if (w < 4) {
+                const uint32_t slot3 = pcnt % 3;
+                const int d = dil[itp.l];
+                const uint32_t dst = sm + C::O_PST + slot3 * 2048 + (uint32_t)(w * 32 + lane) * 16;
+                if (itp.t >= t_end || itp.t < d) {
+                    sts128(dst, make_uint4(0, 0, 0, 0));
+                    mbar_arrive_a(s_pfull + 8 * slot3);
+                } else {
+                    int sl = itp.slot - d; if (sl < 0) sl += slots;
+                    cp_async16(dst, gring - lane16 + (size_t)((uint32_t)(sl * L + itp.l) * rstride) + (size_t)(w * 32 + lane) * 16);
+                    cp_async_arrive_noinc(s_pfull + 8 * slot3);
+                }
+            }
+            pcnt++;
+            advance(itp);
+        };
+
+        uint32_t xa[4][4];
+        uint4 cbA = make_uint4(0, 0, 0, 0), cbB = make_uint4(0, 0, 0, 0);
         float accp[2][4];                              // pre-activation of the coming step: Wprev.x[t-d] + Bh + Lh
         float2 brn;                                    // Bres pair of the coming step
         float4 bh_next; float2 br_next;                // Bh / Bres pairs of the step after (prefetched a layer ahead)
@@ -439,18 +456,22 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
         float sk[C::NSK][4];
 #pragma unroll
         for (int i = 0; i < C::NSK; i++) sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
+        const unsigned char* cptr = gcond + (size_t)t_begin * L * cstride;      // conditioning of step it3 (steps are consecutive in memory)
 
-        // accp <- (Bh + Lh) + Wprev . x[t-d] for the coming step `it1`, whose history / conditioning sit in (pb, cb) and whose
-        // Wprev rides in the SAME ring piece as the current layer's Wcur (`p1`; the very first one comes from global memory);
-        // then refill (pb, cb) with the step `it3`.  Independent of the current layer's data: fills the h exchange.
+        // accp <- (Bh + Lh) + Wprev . x[t-d] for the coming step `it1` (its staged history tile is number `pn`, its conditioning
+        // sits in cbA / cbB by parity); Wprev rides in the SAME ring piece as the current layer's Wcur (`p1`; the very first
+        // one comes from global memory).  Then the conditioning of step it3 is fetched.  Independent of the current layer's data.
         StepIt it1{0, 0, 0}, it3{0, 0, 0};
-        auto prep = [&](uint32_t (&pb)[4][4], uint4& cb, const uint32_t p1, const bool from_global) {
+        uint32_t pn = 0, kp = 0;                       // kp = parity of the running step
+        auto prep = [&](const uint32_t p1, const bool from_global, const bool pf_ok) {
             brn = br_next;
+            const uint4 cb = kp ? cbA : cbB;           // step k consumes the buffer of parity (k + 1) & 1 ...
             {
                 const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
                 accp[0][0] = bh_next.x + c0.x; accp[0][1] = bh_next.y + c0.y; accp[0][2] = bh_next.x + c1.x; accp[0][3] = bh_next.y + c1.y;
                 accp[1][0] = bh_next.z + c2.x; accp[1][1] = bh_next.w + c2.y; accp[1][2] = bh_next.z + c3.x; accp[1][3] = bh_next.w + c3.y;
             }
+            const uint32_t slot3 = pn % 3;
             if (it1.t < t_end) {
                 uint4 bt0, bg0, bt1, bg1;
                 if (from_global) {
@@ -460,14 +481,24 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
                     bt0 = lds128(p1 + C::W_PREV + o_t0); bg0 = lds128(p1 + C::W_PREV + o_g0);
                     bt1 = lds128(p1 + C::W_PREV + o_t0 + 512); bg1 = lds128(p1 + C::W_PREV + o_g0 + 512);
                 }
+                ensure(pf_ok, s_pfull + 8 * slot3, (pn / 3) & 1);
+                uint32_t pb[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) load_a(pb[j], sm + C::O_PST + slot3 * 2048 + j * 512 + lane16);
                 float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};         // second half of K: independent chains
                 hmma(accp[0], pb[0], bt0.x, bt0.y); hmma(accp[1], pb[0], bg0.x, bg0.y); hmma(u0, pb[2], bt1.x, bt1.y); hmma(u1, pb[2], bg1.x, bg1.y);
                 hmma(accp[0], pb[1], bt0.z, bt0.w); hmma(accp[1], pb[1], bg0.z, bg0.w); hmma(u0, pb[3], bt1.z, bt1.w); hmma(u1, pb[3], bg1.z, bg1.w);
 #pragma unroll
                 for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
             }
-            ldP(pb, it3);
-            cb = ldC(it3);
+            pn++;
+            {   // ... and refills it with the conditioning of step k + 3
+                const unsigned char* src = cptr;
+                cptr += cstride;
+                const bool live = it3.t < t_end;       // past the end the stale value is never used (the prep of such a step is skipped)
+                ldg_nc_v4_if(cbA, src, live && kp != 0);
+                ldg_nc_v4_if(cbB, src, live && kp == 0);
+            }
             advance(it1); advance(it3);
             bh_next = *reinterpret_cast<const float4*>(gbl + it1.l * 256);
             br_next = *reinterpret_cast<const float2*>(gbl + it1.l * 256 + 4);
@@ -480,28 +511,30 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
             sts32(sm + C::O_EPBUF + ((g + 8) * EROW + 4 * w + t4) * 4, ep[ys[TU + g + 8] * 32 + 4 * w + t4]);
         }
         StepIt it0{t_begin, 0, t_begin % slots};
+        stage_history(); stage_history(); stage_history();              // history tiles of steps 0, 1, 2
         {
             it1 = it0; it3 = it0;
-            cptr = gcond + (size_t)t_begin * L * cstride;
-            ldP(pbA, it0); cbA = ldC(it0);                              // step 0: consumed right here
-            StepIt i1 = it0; advance(i1);
-            ldP(pbB, i1); cbB = ldC(i1);                                // step 1 -> buffer B
-            advance(it3); advance(it3);                                 // prep() refills buffer A with step 2 ...
+            kp = 1;                                                     // the prologue plays "step -1": consumes cbA (step 0), refills it with step 2
+            cbA = ldg_nc_v4(cptr); cptr += cstride;
+            { StepIt i1 = it0; advance(i1); cbB = i1.t < t_end ? ldg_nc_v4(cptr) : make_uint4(0, 0, 0, 0); cptr += cstride; }
+            advance(it3); advance(it3);
             bh_next = *reinterpret_cast<const float4*>(gbl); br_next = *reinterpret_cast<const float2*>(gbl + 4);
-            prep(pbA, cbA, 0, true);                                    // ... leaving it1 = step 1, it3 = step 3
+            prep(0, true, false);                                       // leaves it1 = step 1, it3 = step 3
+            kp = 0;
         }
         bar_compute();
 
         // ring bookkeeping: a layer step uses slot `sb` of both piece types; the parity of its barriers is `fph`
         uint32_t sb = 0, fph = 0;
 
-        // one layer step.  (pb, cb) hold the history / conditioning of the NEXT step.
-        auto step = [&](const int t, const int l, uint32_t (&pb)[4][4], uint4& cb) {
+        bool ok_f1 = false, ok_f2 = false, ok_pf = false;          // what the look at the coming step's barriers returned
+        // one layer step
+        auto step = [&](const int t, const int l) {
             const uint32_t p1 = sm + C::O_RING1 + sb * C::SLOT1, p2 = sm + C::O_RING2 + sb * C::SLOT2;
             const uint32_t f1 = s_full + sb * 8, f2 = s_full + 16 + sb * 8, e1 = s_empty + sb * 8, e2 = s_empty + 16 + sb * 8;
             const float2 br = brn;
             // ---- a = Wcur.x + [Wprev.x[t-d] + Bh + Lh]   (nv_wavenet.cuh:131-157); the two halves of K as independent chains
-            mbar_wait_a(f1, fph);
+            ensure(ok_f1, f1, fph);
             {
                 const uint4 bt0 = lds128(p1 + o_t0), bg0 = lds128(p1 + o_g0), bt1 = lds128(p1 + o_t0 + 512), bg1 = lds128(p1 + o_g0 + 512);
                 float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -521,7 +554,7 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
             if (tid == 0) TRACE(0, 12);
             // ---- while the other warps finish their part of h: the dilated-history half of the next step's pre-activation
             // (after the last layer: layer 0 of the next sample); then this piece of the ring is free
-            prep(pb, cb, p1, false);
+            prep(p1, false, ok_pf);
             release(e1);
             bar_compute();
             uint32_t ha[4][4];
@@ -530,7 +563,7 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
             if (tid == 0) TRACE(0, 10);
             // ---- x' = Wres.h + Bres + x   (nv_wavenet.cuh:185-207); two half-K chains
             float ra[4] = {0.f, 0.f, 0.f, 0.f}, rb[4] = {0.f, 0.f, 0.f, 0.f};
-            mbar_wait_a(f2, fph);
+            ensure(ok_f2, f2, fph);
             {
                 const uint4 bw0 = lds128(p2 + o_res), bw1 = lds128(p2 + o_res + 512);
                 hmma(ra, ha[0], bw0.x, bw0.y); hmma(rb, ha[2], bw1.x, bw1.y);
@@ -560,6 +593,13 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
                 for (int i = 0; i < C::NSK; i++) hmma(sk[i], ha[2 * jp + 1], bw[i].z, bw[i].w);
             }
             release(e2);
+            stage_history();                           // the history tile of three steps ahead
+            {   // look at the coming step's barriers now; the answers are consumed a barrier later
+                const uint32_t nsb = sb ^ 1, nph = fph ^ sb;
+                ok_f1 = probe(s_full + nsb * 8, nph);
+                ok_f2 = probe(s_full + 16 + nsb * 8, nph);
+                ok_pf = probe(s_pfull + 8 * (pn % 3), (pn / 3) & 1);
+            }
             if (tid == 0) TRACE(0, 15);
             if (DUMP) {
                 const float* pre = gbias + im.b_skpre + (size_t)l * S;
@@ -578,10 +618,10 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
                 for (int j = 0; j < 4; j++) load_a(xa[j], sm + C::O_XBUF + j * 512 + lane16);
             }
             if (tid == 0) TRACE(0, 11);
-            fph ^= sb; sb ^= 1;                        // slot alternates every step, barrier parity every second step
+            fph ^= sb; sb ^= 1; kp ^= 1;               // slot alternates every step, barrier parity every second step
         };
 
-        uint32_t kp = 0, epar = 0;                     // parity of the global step count / of the sample (epbuf buffer)
+        uint32_t epar = 0;                             // parity of the sample (epbuf buffer)
         for (int t = t_begin; t < t_end; t++) {
             // ---------------- embedding (reference.cpp:42-57): x0 = [tanh](embPrev[yPrev] + embCur[yCur]), this warp's 8 channels
             if (tid == 0) TRACE(0, 1);
@@ -612,10 +652,8 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
             for (int j = 0; j < 4; j++) load_a(xa[j], sm + C::O_XBUF + j * 512 + lane16);
             if (tid == 0) TRACE(0, 2);
 
-            for (int l = 0; l < L; l++) {
-                if (kp == 0) step(t, l, pbB, cbB); else step(t, l, pbA, cbA);
-                kp ^= 1;
-            }
+            for (int l = 0; l < L; l++) step(t, l);
+            ok_f1 = ok_f2 = false;                     // those looks were at slots the output pieces use first (same parity): stale
 
             // ---------------- relu(skip + bias) -> Zs -> Za   (reference.cpp:93-104)
 #pragma unroll
@@ -684,6 +722,10 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
             }
             bar_compute();
             if (tid == 0) TRACE(0, 22);
+            if (t + 1 < t_end) {                       // every output piece is consumed: the first pieces of the next sample
+                ok_f1 = probe(s_full + sb * 8, fph);
+                ok_f2 = probe(s_full + 16 + sb * 8, fph);
+            }
             // ---------------- softmax + categorical sample (matrix.cpp:167-183, reference.cpp:106-121): warp w serves
             // utterances 2w and 2w+1; lane holds 8 consecutive classes of each
             {
