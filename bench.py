@@ -229,6 +229,33 @@ def batch_sweep(nw, torch, args, dtype, T, peak, alg, n_samples=4000):
     return out
 
 
+def conditioning_producer_timing(eng, torch, args, T):
+    """mel frames -> upsampling ConvTranspose1d(80, 80, 800, 200) -> 1x1 cond_layers -> the engine's conditioning
+    store, on the device (nvwn_set_conditioning_from_features), for the whole utterance batch of this run; one-off per batch."""
+    L, R = MODEL["L"], MODEL["R"]
+    B, N = args.batch, args.samples
+    C, window, stride = 80, 800, 200                         # pytorch/config.json of the reference
+    frames = N // stride
+    if frames < 1:
+        return None
+    g = torch.Generator(device="cuda"); g.manual_seed(SEED + 5)
+    rnd = lambda *shape, s=1.0: torch.randn(shape, generator=g, device="cuda", dtype=torch.float32) * s
+    feats, wu, bu = rnd(B, C, frames), rnd(C, C, window, s=0.02), rnd(C, s=0.01)
+    wc, bc = rnd(L * 2 * R, C, s=0.05), rnd(L * 2 * R, s=0.05)
+    best = None
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.set_conditioning_from_features(feats, wu, bu, wc, bc, stride)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out_bytes = frames * stride * L * B * 2 * R * T
+    return {"ms": best * 1e3, "samples": frames * stride, "batch": B, "mel_channels": C, "window": window, "stride": stride,
+            "store_GB": out_bytes / 1e9, "store_GB_per_s": out_bytes / 1e9 / best,
+            "fraction_of_generation_time": None, "note": "synchronous one-off producer (not overlapped with generation in this measurement)"}
+
+
 def reference_gpu_kernels(args, our_khz, n_samples=600):
     """The reference's OWN CUDA kernels (oracle/_ref/ref_gpu_harness: unmodified nv_wavenet.cuh rebuilt for sm_100a), same model,
     same batch, same box, timed like nv_wavenet_perf.cu:67-87 -- the GPU baseline next to the headline.  Test infrastructure:
@@ -451,6 +478,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_extra:
         extra["batch_sweep"] = batch_sweep(nw, torch, args, dtype, T, peak, alg)
         extra["reference_gpu_kernels"] = reference_gpu_kernels(args, N / (elapsed_ms / args.steps))
+        extra["conditioning_producer"] = conditioning_producer_timing(eng, torch, args, T)
     line = {
         "metric": metric_name(), "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,

@@ -175,6 +175,18 @@ __device__ __forceinline__ bool mbar_test_a(uint32_t bar, uint32_t parity)      
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// three looks issued back to back: their ~90-cycle latencies overlap
+__device__ __forceinline__ void mbar_try3_a(uint32_t b1, uint32_t p1, uint32_t b2, uint32_t p2, uint32_t b3, uint32_t p3, bool& o1, bool& o2, bool& o3)
+{
+    uint32_t r1, r2, r3;
+    asm volatile("{\n\t.reg .pred q1, q2, q3;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
+                 "selp.u32 %0, 1, 0, q1;\n\tselp.u32 %1, 1, 0, q2;\n\tselp.u32 %2, 1, 0, q3;\n\t}"
+                 : "=r"(r1), "=r"(r2), "=r"(r3) : "r"(b1), "r"(p1), "r"(b2), "r"(p2), "r"(b3), "r"(p3) : "memory");
+    o1 = r1 != 0; o2 = r2 != 0; o3 = r3 != 0;
+}
 static __device__ __noinline__ void lat_timeout(uint32_t bar, uint32_t parity)
 {
     printf("wn_lat: mbarrier wait timed out: block %d thread %d barrier@0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
@@ -596,9 +608,7 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
             stage_history();                           // the history tile of three steps ahead
             {   // look at the coming step's barriers now; the answers are consumed a barrier later
                 const uint32_t nsb = sb ^ 1, nph = fph ^ sb;
-                ok_f1 = probe(s_full + nsb * 8, nph);
-                ok_f2 = probe(s_full + 16 + nsb * 8, nph);
-                ok_pf = probe(s_pfull + 8 * (pn % 3), (pn / 3) & 1);
+                mbar_try3_a(s_full + nsb * 8, nph, s_full + 16 + nsb * 8, nph, s_pfull + 8 * (pn % 3), (pn / 3) & 1, ok_f1, ok_f2, ok_pf);
             }
             if (tid == 0) TRACE(0, 15);
             if (DUMP) {

@@ -231,6 +231,34 @@ def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
                 assert np.abs(ag[k] - ao[k]).max() <= tol * sc, f"{k}: {np.abs(ag[k] - ao[k]).max() / sc}"
 
 
+@pytest.mark.parametrize("shape", [
+    (32, 128, 256, 6, 5, 14, 4),          # R32: reference shape (README.md:7-10); the mma kernels are R64-only
+    (128, 256, 256, 4, 3, 10, 4),         # R128
+    (64, 128, 512, 4, 3, 10, 2),          # A = 512 (nv_wavenet_test.cu:391-394)
+    (64, 256, 256, 3, 4, 12, 4),          # L < 4: below the latency kernel's prefetch depth
+])
+def test_fp16_fallback_shapes_use_the_stream_kernel(shape, monkeypatch):
+    """fp16 on shapes outside the tensor-core kernels' set: AUTO must fall back to the CUDA-core stream kernel (no error, no other
+    path), and its logits must meet the same fp16 tolerance against the oracle."""
+    for k in ("NVWN_FP16_KERNEL", "NVWN_TC_TILE", "NVWN_TC_NODUP", "NVWN_TC_FUSED"):
+        monkeypatch.delenv(k, raising=False)
+    R, S, A, L, B, N, md = shape
+    w = refgen.lively_inputs(40 + R + A, R, S, A, L, B, N)
+    o = cpu_oracle(w, L, B, N, R, S, A, md)
+    forced = o.run(N, B)
+    e = gpu_engine(w, L, B, N, R, S, A, md, dtype=nw.FP16)
+    e.set_forced(forced)
+    y = np.zeros((B, N), np.int32)
+    e.run(N, B, y, dump_activations=True); e.synchronize()
+    expect = 17 if (R, A) == (64, 256) and L < 4 else 16          # R64/A256 with L < 4: the tensor-core kernel still applies
+    assert e.launch_info()["kernel"] == expect
+    o16 = cpu_oracle(w, L, B, N, R, S, A, md, prec=po.PREC_FP16); o16.set_forced(forced); o16.run(N, B)
+    ag = e.activations()
+    _logit_check(o16.get_za(), ag["za"], 1e-2, mean_rel=3e-4)
+    _logit_check(o.get_za(), ag["za"], 1e-2)
+    _check_sampled_index(ag["p"], w["selectors"][N - 1], y[:, N - 1])
+
+
 def _run_range(e, init, count, N, B, y=None):
     """run_partial over samples [init, init+count) of an N-sample batch (the reference's run_partial + samples_per_chunk)."""
     e._samples_per_chunk = count
