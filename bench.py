@@ -304,7 +304,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L, R, S, A, md = MODEL["L"], MODEL["R"], MODEL["S"], MODEL["A"], MODEL["max_dilation"]
     B, N = args.batch, args.samples
-    dtype = nw.FP16 if args.dtype == "fp16" else nw.FP32
+    dtype = {"fp16": nw.FP16, "fp32": nw.FP32, "fp32fast": nw.FP32_FAST}[args.dtype]
     T = 2 if dtype == nw.FP16 else 4
     eng = nw.NVWavenetInfer(L, md, B, N, R=R, S=S, A=A, dtype=dtype)
 
@@ -482,7 +482,7 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": metric_name(), "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == nw.FP16 else "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == nw.FP16 else "f32", "arithmetic": {nw.FP16: "fp16 inputs, fp32 accumulate", nw.FP32: "fp32, bit-exact to the reference CPU model", nw.FP32_FAST: "fp32, reference GPU kernels' order (FMA, 2 partial sums)"}[dtype],
         "data": "synthetic", "config": workload_config(args, world * B),
         "khz_per_utterance": N / (elapsed_ms / args.steps), "clocks": clk, "e2e": e2e, "gpu_launches": launches,
         "launch": {k: info[k] for k in ("kernel", "grid", "block", "smem_bytes", "batch_per_cta")},
@@ -502,7 +502,7 @@ def main():
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS), help="BASELINE.json configuration (C3 = headline)")
     ap.add_argument("--batch", type=int, default=None, help="utterances per GPU (default: the configuration's)")
     ap.add_argument("--samples", type=int, default=16000)
-    ap.add_argument("--dtype", default=None, choices=["fp16", "fp32"])
+    ap.add_argument("--dtype", default=None, choices=["fp16", "fp32", "fp32fast"])
     ap.add_argument("--no-extra", action="store_true", help="skip the batch sweep and the reference-GPU-kernel runs")
     ap.add_argument("--cpu-samples", type=int, default=96, help="samples per utterance of the bounded CPU-reference leg")
     ap.add_argument("--e2e-chunk", type=int, default=1000)

@@ -24,7 +24,10 @@ extern "C" {
 
 typedef struct nvwn_engine nvwn_engine;
 
-enum { NVWN_FP32 = 0, NVWN_FP16 = 1 };          /* T_data=float / T_data=half of the reference */
+enum { NVWN_FP32 = 0, NVWN_FP16 = 1,          /* T_data=float (bit-exact to the reference CPU model) / T_data=half of the reference */
+       NVWN_FP32_FAST = 2 };                  /* fp32 in the reference GPU kernels' arithmetic: FMA, two interleaved partial sums per dot
+                                                 product (matrix_math.cuh:80-117), float libm tanh/exp -- agrees with the CPU model like the
+                                                 reference's own kernels do (nv_wavenet_test.cu:273-298), about twice as fast */
 enum { NVWN_EINVAL = -1, NVWN_EUNSUPPORTED = -2, NVWN_ENOMEM = -3 };
 /* kernel selection; the reference's Implementation enum values 0..4 are accepted and map to AUTO */
 enum { NVWN_KERNEL_AUTO = 0, NVWN_KERNEL_STREAM = 16, NVWN_KERNEL_TENSORCORE = 17, NVWN_KERNEL_LATENCY = 18 };

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libwavenet_infer.so")
 
-FP32, FP16 = 0, 1
+FP32, FP16, FP32_FAST = 0, 1, 2
 KERNEL_AUTO, KERNEL_STREAM, KERNEL_TENSORCORE, KERNEL_LATENCY = 0, 16, 17, 18
 
 _vp = C.c_void_p

@@ -38,7 +38,7 @@ struct WnLaunchInfo {
 };
 
 // stream kernel (wn_stream_kernel.cu): CUDA-core, one CTA per batch tile, weights streamed from L2.
-cudaError_t wn_launch_stream(const WnParams& p, bool fp16, cudaStream_t stream, WnLaunchInfo* info);
+cudaError_t wn_launch_stream(const WnParams& p, int contract, cudaStream_t stream, WnLaunchInfo* info);   // 0 fp32 exact, 1 fp16, 2 fp32 fast
 bool wn_stream_supported(int R, int S, int A, bool fp16);
 
 // conversions (wn_convert.cu)

@@ -114,7 +114,7 @@ namespace {
 int upload(nvwn_engine* e, void* dst, const float* src, size_t n, cudaStream_t stream = 0)
 {
     if (n == 0) return 0;
-    if (e->dtype == NVWN_FP32) {
+    if (e->dtype != NVWN_FP16) {
         CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDefault, stream));
         return 0;
     }
@@ -202,7 +202,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
 {
     if (!out) return fail(NVWN_EINVAL, "nvwn_create: out is NULL");
     *out = nullptr;
-    if (dtype != NVWN_FP32 && dtype != NVWN_FP16) return fail(NVWN_EINVAL, "nvwn_create: dtype must be NVWN_FP32 or NVWN_FP16");
+    if (dtype != NVWN_FP32 && dtype != NVWN_FP16 && dtype != NVWN_FP32_FAST) return fail(NVWN_EINVAL, "nvwn_create: dtype must be NVWN_FP32, NVWN_FP16 or NVWN_FP32_FAST");
     if (num_layers < 1 || max_dilation < 1 || batch_size < 1 || num_samples < 1) return fail(NVWN_EINVAL, "nvwn_create: sizes must be positive");
     if (!wn_stream_supported(R, S, A, dtype == NVWN_FP16))
         return fail(NVWN_EUNSUPPORTED, "nvwn_create: unsupported channel counts (R,S) must be one of (32,128) (64,128) (64,256) (128,256); A a multiple of 32");
@@ -513,7 +513,7 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
             }
             CK(wn_launch_tc(p, e->tc_image, e->tc_tile, e->tc_fused, stream, &e->last));
         } else {
-            CK(wn_launch_stream(p, e->dtype == NVWN_FP16, stream, &e->last));
+            CK(wn_launch_stream(p, e->dtype == NVWN_FP16 ? 1 : (e->dtype == NVWN_FP32_FAST ? 2 : 0), stream, &e->last));
         }
         e->launches++;
     }

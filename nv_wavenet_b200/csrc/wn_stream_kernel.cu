@@ -48,16 +48,36 @@ template <> struct Num<__half> {
     static __device__ __forceinline__ float sigmoid_(float v) { return wn::sigmoidf_fast(v); }
 };
 
+// fp32 in the REFERENCE GPU KERNELS' arithmetic (NVWN_FP32_FAST): fused multiply-add, two interleaved partial sums per dot
+// product (GEMM<R,2>, matrix_math.cuh:80-117), single-precision libm tanh / exp.  Not bit-identical to the CPU model -- it
+// agrees with it like the reference's own kernels do (sampled indices equal unless a selector falls within rounding of a
+// class boundary; nv_wavenet_test.cu:273-298 tolerances on the activations) -- but free of the 8-cycle-per-term serial chain.
+struct NumFast32 {
+    static constexpr bool exact = false;
+    static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+    static __device__ __forceinline__ float q(float v) { return v; }
+    static __device__ __forceinline__ float mac(float acc, float w, float x) { return fmaf(w, x, acc); }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float tanh_(float v) { return tanhf(v); }
+    static __device__ __forceinline__ float sigmoid_(float v) { return 1.f / (1.f + expf(-v)); }
+};
+template <typename TD, bool FAST> struct NumSel { using type = Num<TD>; };
+template <> struct NumSel<float, true> { using type = NumFast32; };
+
 // acc[b] = sum_k W[row + k*M] * xs[b][k], k ascending (matrix.cpp:85-102 order).
 // KB weights are requested back to back before the first use, so the L2 latency is paid once per
 // KB columns instead of once per 8.
-template <typename TD, int BT, int KB>
+template <typename TD, int BT, int KB, bool FAST>
 __device__ __forceinline__ void dot_cols(const TD* __restrict__ W, int M, int K, int row,
                                          const float* __restrict__ xs, float (&acc)[BT])
 {
-    using N = Num<TD>;
+    using N = typename NumSel<TD, FAST>::type;
+    float odd[BT];                                   // second partial sum of the non-exact contracts (odd k)
 #pragma unroll
-    for (int b = 0; b < BT; b++) acc[b] = 0.f;
+    for (int b = 0; b < BT; b++) { acc[b] = 0.f; odd[b] = 0.f; }
     const TD* wp = W + row;
 #pragma unroll 1
     for (int k0 = 0; k0 < K; k0 += KB) {
@@ -69,11 +89,21 @@ __device__ __forceinline__ void dot_cols(const TD* __restrict__ W, int M, int K,
 #pragma unroll
             for (int b = 0; b < BT; b++) {
                 const float4 xa = *reinterpret_cast<const float4*>(xs + b * K + k0 + j);
-                float a = acc[b];
-                a = N::mac(a, w[j], xa.x); a = N::mac(a, w[j + 1], xa.y); a = N::mac(a, w[j + 2], xa.z); a = N::mac(a, w[j + 3], xa.w);
-                acc[b] = a;
+                if (N::exact) {
+                    float a = acc[b];
+                    a = N::mac(a, w[j], xa.x); a = N::mac(a, w[j + 1], xa.y); a = N::mac(a, w[j + 2], xa.z); a = N::mac(a, w[j + 3], xa.w);
+                    acc[b] = a;
+                } else {
+                    float a = acc[b], o = odd[b];
+                    a = N::mac(a, w[j], xa.x); o = N::mac(o, w[j + 1], xa.y); a = N::mac(a, w[j + 2], xa.z); o = N::mac(o, w[j + 3], xa.w);
+                    acc[b] = a; odd[b] = o;
+                }
             }
         }
+    }
+    if (!N::exact) {
+#pragma unroll
+        for (int b = 0; b < BT; b++) acc[b] += odd[b];
     }
 }
 
@@ -89,10 +119,10 @@ __host__ __device__ constexpr size_t stream_smem_floats(int A, int L)
     return (size_t)BT * (3 * R + 4 * R + R + 2 * S + 3 * A) + BT * 4 + BT * 2 + L + 4;
 }
 
-template <typename TD, int R, int S, int BT>
+template <typename TD, int R, int S, int BT, bool FAST>
 __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnParams p)
 {
-    using N = Num<TD>;
+    using N = typename NumSel<TD, FAST>::type;
     constexpr int NT = Shape<R, S>::NT;
     constexpr int NACT = 2 * R * BT;
     constexpr int ACT_PER = (NACT + NT - 1) / NT;
@@ -213,7 +243,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
                 const int row = cur ? tid - 2 * R : tid;
                 const TD* W = (cur ? Wcur : Wprev) + (size_t)l * 2 * R * R;
                 float acc[BT];
-                dot_cols<TD, BT, KBR>(W, 2 * R, R, row, cur ? xq : xp, acc);
+                dot_cols<TD, BT, KBR, FAST>(W, 2 * R, R, row, cur ? xq : xp, acc);
                 float* dst = cur ? ac : ap;
 #pragma unroll
                 for (int b = 0; b < BT; b++) dst[b * 2 * R + row] = acc[b];
@@ -249,7 +279,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
                 const TD* W = is_res ? Wres + (size_t)l * R * R : Wskip + (size_t)l * S * R;
                 const float bias = is_res ? N::ld(Bres + (size_t)l * R + row) : N::ld(Bskip + (size_t)l * S + row);
                 float acc[BT];
-                dot_cols<TD, BT, KBR>(W, is_res ? R : S, R, row, hq, acc);
+                dot_cols<TD, BT, KBR, FAST>(W, is_res ? R : S, R, row, hq, acc);
                 if (is_res) {
 #pragma unroll
                     for (int b = 0; b < BT; b++) {
@@ -278,7 +308,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
         for (int row = tid; row < A; row += NT) {
             float acc[BT];
             const float bias = N::ld(Bzs + row);
-            dot_cols<TD, BT, 32>(Wzs, A, S, row, skq, acc);
+            dot_cols<TD, BT, 32, FAST>(Wzs, A, S, row, skq, acc);
 #pragma unroll
             for (int b = 0; b < BT; b++) {
                 float v = N::add(acc[b], bias);
@@ -291,7 +321,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
         for (int row = tid; row < A; row += NT) {
             float acc[BT];
             const float bias = N::ld(Bza + row);
-            dot_cols<TD, BT, 32>(Wza, A, A, row, zsq, acc);
+            dot_cols<TD, BT, 32, FAST>(Wza, A, A, row, zsq, acc);
 #pragma unroll
             for (int b = 0; b < BT; b++) {
                 const float v = N::add(acc[b], bias);
@@ -402,12 +432,12 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
     if (tid < BT) { p.yPrev[b0 + tid] = ysm[tid * 2]; p.yCur[b0 + tid] = ysm[tid * 2 + 1]; }
 }
 
-template <typename TD, int R, int S, int BT>
+template <typename TD, int R, int S, int BT, bool FAST>
 cudaError_t launch_one(const WnParams& p, cudaStream_t stream, WnLaunchInfo* info)
 {
     constexpr int NT = Shape<R, S>::NT;
     const size_t smem = stream_smem_floats<R, S, BT>(p.A, p.L) * sizeof(float);
-    auto kfn = wn_stream_kernel<TD, R, S, BT>;
+    auto kfn = wn_stream_kernel<TD, R, S, BT, FAST>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = p.B / BT;
@@ -416,23 +446,23 @@ cudaError_t launch_one(const WnParams& p, cudaStream_t stream, WnLaunchInfo* inf
     return cudaGetLastError();
 }
 
-template <typename TD, int R, int S>
+template <typename TD, int R, int S, bool FAST>
 cudaError_t launch_bt(const WnParams& p, int bt, cudaStream_t stream, WnLaunchInfo* info)
 {
     switch (bt) {
-        case 4: return launch_one<TD, R, S, 4>(p, stream, info);
-        case 2: return launch_one<TD, R, S, 2>(p, stream, info);
-        default: return launch_one<TD, R, S, 1>(p, stream, info);
+        case 4: return launch_one<TD, R, S, 4, FAST>(p, stream, info);
+        case 2: return launch_one<TD, R, S, 2, FAST>(p, stream, info);
+        default: return launch_one<TD, R, S, 1, FAST>(p, stream, info);
     }
 }
 
-template <typename TD>
+template <typename TD, bool FAST>
 cudaError_t launch_shape(const WnParams& p, int bt, cudaStream_t stream, WnLaunchInfo* info)
 {
-    if (p.R == 32 && p.S == 128) return launch_bt<TD, 32, 128>(p, bt, stream, info);
-    if (p.R == 64 && p.S == 128) return launch_bt<TD, 64, 128>(p, bt, stream, info);
-    if (p.R == 64 && p.S == 256) return launch_bt<TD, 64, 256>(p, bt, stream, info);
-    if (p.R == 128 && p.S == 256) return launch_bt<TD, 128, 256>(p, bt, stream, info);
+    if (p.R == 32 && p.S == 128) return launch_bt<TD, 32, 128, FAST>(p, bt, stream, info);
+    if (p.R == 64 && p.S == 128) return launch_bt<TD, 64, 128, FAST>(p, bt, stream, info);
+    if (p.R == 64 && p.S == 256) return launch_bt<TD, 64, 256, FAST>(p, bt, stream, info);
+    if (p.R == 128 && p.S == 256) return launch_bt<TD, 128, 256, FAST>(p, bt, stream, info);
     return cudaErrorInvalidValue;
 }
 
@@ -458,10 +488,13 @@ static int pick_bt(const WnParams& p, bool fp16)
     return bt;
 }
 
-cudaError_t wn_launch_stream(const WnParams& p, bool fp16, cudaStream_t stream, WnLaunchInfo* info)
+// contract: 0 = fp32 bit-exact (CPU model's operation order), 1 = fp16 storage, 2 = fp32 in the reference GPU kernels' arithmetic
+cudaError_t wn_launch_stream(const WnParams& p, int contract, cudaStream_t stream, WnLaunchInfo* info)
 {
+    const bool fp16 = contract == 1;
     if (!wn_stream_supported(p.R, p.S, p.A, fp16)) return cudaErrorInvalidValue;
     const int bt = pick_bt(p, fp16);
     if (info) info->kernel = 16;
-    return fp16 ? launch_shape<__half>(p, bt, stream, info) : launch_shape<float>(p, bt, stream, info);
+    if (fp16) return launch_shape<__half, false>(p, bt, stream, info);
+    return contract == 2 ? launch_shape<float, true>(p, bt, stream, info) : launch_shape<float, false>(p, bt, stream, info);
 }

@@ -108,6 +108,49 @@ def test_fp32_no_tanh_embed_and_forced_history():
     assert_acts_bit_equal(o.activations(), e.activations())
 
 
+_FAST_RUNS = list({r[3:6]: r for r in reversed(RUNS)}.values())          # the first reference run of every (R, S, A) shape
+
+
+@pytest.mark.parametrize("run", _FAST_RUNS, ids=lambda r: r[0])
+def test_fp32_fast_contract_on_reference_test_runs(run):
+    """NVWN_FP32_FAST (FMA, two interleaved partial sums, float libm -- the arithmetic of the reference's GPU kernels): on the
+    reference's own test runs the sampled indices equal the CPU model's and the activations stay within the reference test's own
+    tolerances (nv_wavenet_test.cu:273-298), which is all the reference's kernels promise."""
+    key, seed, i, R, S, A, L = run
+    B, N, md = common.B_REF, common.N_REF, common.MAXDIL_REF
+    w = common.reference_inputs(seed, i)
+    g = common.golden()
+    e = gpu_engine(w, L, B, N, R, S, A, md, dtype=nw.FP32_FAST)
+    y = np.zeros((B, N), np.int32)
+    e.run(N, B, y, dump_activations=True); e.synchronize()
+    assert np.array_equal(y, g[key + "/y"][0]), "sampled indices differ from the reference CPU model"
+    ag = e.activations()
+    assert common.matrix_compare_ok(g[key + "/za"][0], ag["za"], 1e-4)
+    assert common.matrix_compare_ok(g[key + "/p"][0], ag["p"], 1e-3)
+    assert common.matrix_compare_ok(g[key + "/xt_last"][0], ag["xt"][-1], 1e-2)
+    assert common.matrix_compare_ok(g[key + "/skip_last"][0], ag["skip"][-1], 1e-2, relu=True)
+
+
+def test_fp32_fast_contract_lively_and_chunked():
+    """Same contract on lively weights at the C4 shape (L30 R128 S256, maxDil 512): logits within 1e-4 of the bit-exact kernel at
+    matched history, chunked == unchunked, and the free-running trajectories agree except where a selector sits on a boundary."""
+    R, S, A, L, B, N, md = 128, 256, 256, 30, 4, 80, 512
+    w = refgen.lively_inputs(17, R, S, A, L, B, N)
+    ex = gpu_engine(w, L, B, N, R, S, A, md)
+    ye = np.zeros((B, N), np.int32); ex.run(N, B, ye, dump_activations=True); ex.synchronize()
+    fa = gpu_engine(w, L, B, N, R, S, A, md, dtype=nw.FP32_FAST)
+    fa.set_forced(ye)
+    yf = np.zeros((B, N), np.int32); fa.run(N, B, yf, dump_activations=True); fa.synchronize()
+    za_e, za_f = ex.get_za(), fa.get_za()
+    assert np.abs(za_f - za_e).max() <= 1e-4 * np.abs(za_e).max()
+    assert (yf == ye).mean() > 0.99
+    fa.set_forced(None); fa.reset_history()
+    y1 = np.zeros((B, N), np.int32); fa.run(N, B, y1); fa.synchronize()
+    fa.reset_history(); y2 = np.zeros((B, N), np.int32)
+    fa.run_chunks(7, lambda *a: None, N, B, y2); fa.synchronize()
+    assert np.array_equal(y1, y2)
+
+
 def test_fp32_properties_at_full_model_size():
     """C3-sized model (L20 R64 S256 A256, maxDil 512), longer than the oracle can follow cheaply:
     chunked == unchunked, batch shards == whole batch, run-to-run determinism."""
