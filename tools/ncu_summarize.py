@@ -1,7 +1,7 @@
 """Summarise ncu outputs into profiles/ (run in the build container, reads gpurun_out/).
 
   python tools/ncu_summarize.py launches gpurun_out/r01_launches.csv profiles/r01_tc_launches_summary.csv "<command>"
-  python tools/ncu_summarize.py full gpurun_out/r01_tc_full.ncu-rep profiles/r01_tc_ncu_full_summary.json <units> "<command>"
+  python tools/ncu_summarize.py full gpurun_out/r01_tc_full.ncu-rep profiles/r01_tc_ncu_full_summary.json <units> "<command>" [config kernel_id samples batch]
 """
 import csv
 import io
@@ -50,7 +50,7 @@ def launches(src, dst, command):
     print(open(dst).read())
 
 
-def full(src, dst, units, command):
+def full(src, dst, units, command, config=None, kernel_id=None, samples=None, batch=None):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, unit_row, val = rows[0], rows[1], rows[2]
@@ -70,6 +70,7 @@ def full(src, dst, units, command):
     rd = to_bytes(m["dram__bytes_read.sum"]["value"], m["dram__bytes_read.sum"]["unit"])
     wr = to_bytes(m["dram__bytes_write.sum"]["value"], m["dram__bytes_write.sum"]["unit"])
     res = {"kernel": val[hdr.index("Kernel Name")], "capture": command, "units_in_capture": units,
+           "config": config, "kernel_id": kernel_id, "capture_samples": samples, "capture_batch": batch,
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_unit": round((rd + wr) / units, 2),
            "metrics": {**m, "top_stalls_per_issue": top}}
     json.dump(res, open(dst, "w"), indent=1)
@@ -80,4 +81,5 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
-        full(sys.argv[2], sys.argv[3], int(sys.argv[4]), sys.argv[5])
+        extra = sys.argv[6:10]
+        full(sys.argv[2], sys.argv[3], int(sys.argv[4]), sys.argv[5], *( [extra[0], int(extra[1]), int(extra[2]), int(extra[3])] if len(extra) == 4 else []))
