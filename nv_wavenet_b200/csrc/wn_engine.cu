@@ -41,7 +41,7 @@ cudaError_t wn_lat_cond_convert(void* dst, const float* src_dev, int first_sampl
 cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream);
 cudaError_t wn_lat_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
 cudaError_t wn_tc_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int TU, int L, int B, cudaStream_t stream);
-cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, cudaStream_t stream, WnLaunchInfo* info);
+cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, bool cluster, cudaStream_t stream, WnLaunchInfo* info);
 
 namespace {
 
@@ -96,6 +96,7 @@ struct nvwn_engine {
     bool tc_mode = false;                    // decided once at creation: conditioning + history use the tiled layouts
     int tc_tile = 64;                        // utterances per tensor-core tile and its schedule: resolved ONCE at creation (the
     bool tc_fused = false;                   // conditioning store, the history ring and every launch depend on them)
+    bool lat_cluster = true;                 // latency mode: a two-CTA cluster per tile while 2 x tiles fit one wave (NVWN_LAT_CLUSTER=0 disables; read once)
     bool lat_mode = false;                   // decided once at creation: latency-mode kernel (fragment-ordered layouts); tc_image holds its weight image
 
     float* lut_f = nullptr;                  // mu-law decode tables (nvwn_get_audio): A floats, then 2 x A int16 (wrap / saturate)
@@ -243,6 +244,7 @@ int nvwn_create(nvwn_engine** out, int dtype, int R, int S, int A, int num_layer
     {
         const int k = decide_fp16_kernel(dtype, impl, R, S, A, num_layers, batch_size);
         e->tc_mode = k == 1; e->lat_mode = k == 2;
+        if (const char* v = getenv("NVWN_LAT_CLUSTER")) e->lat_cluster = atoi(v) != 0;
         if (e->tc_mode) { e->tc_tile = wn_tc_tile_utt(batch_size, S); e->tc_fused = wn_tc_fused_default() || e->tc_tile == 32; }
     }
     ALLOC(e->Lh, e->tc_mode ? wn_tc_cond_bytes(e->tc_tile, num_layers, batch_size, num_samples)
@@ -503,7 +505,7 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
                 CK(wn_lat_pack(e->tc_image, p, stream));
                 e->tc_dirty = false;
             }
-            CK(wn_launch_lat(p, e->tc_image, e->B, stream, &e->last));
+            CK(wn_launch_lat(p, e->tc_image, e->B, e->lat_cluster && (batch_size + 15) / 16 <= 74, stream, &e->last));
         } else if (e->tc_mode) {
             if (batch_size != e->B)
                 return fail(NVWN_EINVAL, "nvwn_run_partial: the tensor-core path needs batch_size equal to the engine's batch size");

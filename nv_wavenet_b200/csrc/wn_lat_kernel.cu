@@ -814,6 +814,552 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
 #undef TRACE
 }
 
+// ================================================================================================ two-CTA cluster variant
+// The single-CTA kernel above runs at ~83 % of its SM's shared-memory bandwidth (per layer step: 72 KB written by TMA, 72 KB of
+// B fragments and 48 KB of A fragments read back; ncu: 0.57 LSU wavefronts per cycle + the TMA writes).  Here one 16-utterance tile
+// is served by a CLUSTER OF TWO CTAs on two SMs, which halves that traffic per SM:
+//   rank 0 "chain": embedding, cur / prev / res GEMMs, gate, history ring          ring pieces [Wcur_l | Wprev_l+1 | Wres_l] (40 KB)
+//   rank 1 "tail":  skip GEMM (one step behind, off the chain), Zs, Za, softmax, sampling      ring pieces Wskip_l and the output pieces
+// h goes chain -> tail through distributed shared memory (st.shared::cluster into a double-buffered tile + a remote mbarrier
+// arrive; the tail returns the buffer the same way); the sampled indices come back the same way once per sample.
+constexpr int NTC = NCT + 32;
+
+template <int S>
+struct CfgC {
+    using C = Cfg<S>;
+    static constexpr uint32_t PIECE0 = 40960;                              // chain: [Wcur | Wprev | Wres]
+    static constexpr uint32_t SLOT1 = 32768;                               // tail: Wskip_l (S x 128 B) or an output piece
+    static constexpr int NSLOT1 = 4;
+    // chain CTA
+    static constexpr uint32_t C_RING = 0;                                  // 2 x PIECE0
+    static constexpr uint32_t C_EMB = 2 * PIECE0;
+    static constexpr uint32_t C_EPBUF = C_EMB + A * EROW * 4;
+    static constexpr uint32_t C_PST = C_EPBUF + 2 * TU * EROW * 4;
+    static constexpr uint32_t C_XBUF = C_PST + 3 * 2048;
+    static constexpr uint32_t C_HBUF = C_XBUF + 2048;
+    static constexpr uint32_t C_DIL = C_HBUF + 2048;
+    static constexpr uint32_t C_END = C_DIL + MAXL * 4;
+    // tail CTA
+    static constexpr uint32_t T_RING = 0;                                  // NSLOT1 x SLOT1
+    static constexpr uint32_t T_BOUT = NSLOT1 * SLOT1;
+    static constexpr uint32_t T_HBUF = T_BOUT + (S + 2 * A) * 4;           // 2 x 2 KB, written by the chain CTA
+    static constexpr uint32_t T_OB0 = T_HBUF + 2 * 2048;
+    static constexpr uint32_t T_OB1 = T_OB0 + (S / 16) * 512;
+    static constexpr uint32_t T_LBUF = T_OB1 + (A / 16) * 512;
+    static constexpr uint32_t T_END = T_LBUF + TU * LROW * 4;
+    // common tail of both maps (same offsets in both CTAs, so that remote addresses are computed with mapa on local ones)
+    static constexpr uint32_t O_YS = (C_END > T_END ? C_END : T_END);
+    static constexpr uint32_t O_BAR = O_YS + 2 * TU * 4;
+    static constexpr uint32_t SMEM = O_BAR + 24 * 8;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t raddr, uint32_t a, uint32_t b) { asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" ::"r"(raddr), "r"(a), "r"(b) : "memory"); }
+__device__ __forceinline__ void st_cluster_u32(uint32_t raddr, uint32_t a) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(a) : "memory"); }
+// remote stores that complete bytes on a remote mbarrier (data and signal travel together: no release fence on the sender)
+__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t a, uint32_t b, uint32_t rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1,%2}, [%3];" ::"r"(raddr), "r"(a), "r"(b), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_u32(uint32_t raddr, uint32_t a, uint32_t rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(a), "r"(rbar) : "memory");
+}
+// "this buffer is free again": no data behind it, so no release ordering is paid for
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) { asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory"); }
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_cluster(bar, parity))
+        if (++spins > (1u << 24)) lat_timeout(bar, parity);
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int S, bool DUMP>
+__global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const unsigned char* __restrict__ img, const int ntiles_alloc)
+{
+    using C = Cfg<S>;
+    using M = CfgC<S>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sm = smem_u32(smem_raw);
+    const int L = p.L, B = p.B;
+    const LatImage im = lat_image(S, L);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const bool is_chain = crank == 0;
+    const int tile = blockIdx.x >> 1;
+    const int slots = p.maxDil + 1;
+    const int t_begin = p.init_sample, t_end = p.init_sample + p.count;
+    const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
+    constexpr int NQ = C::NQ_ZS + C::NQ_ZA;
+
+    // barriers (same offsets in both CTAs): ring full[4] / empty[4] (the chain uses two of each), pfull[3] (chain), hfull[2] (in the
+    // tail CTA, arrived by the chain's warps), hfree[2] and yfull (in the chain CTA, arrived by the tail's warps)
+    const uint32_t s_full = sm + M::O_BAR, s_empty = s_full + 32, s_pfull = s_full + 64, s_hfull = s_full + 88, s_hfree = s_full + 104, s_yfull = s_full + 120;
+    int* ys = reinterpret_cast<int*>(smem_raw + M::O_YS);
+    const uint32_t peer = crank ^ 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; i++) { mbar_init_a(s_full + 8 * i, 1); mbar_init_a(s_empty + 8 * i, NCW); }
+        for (int i = 0; i < 3; i++) mbar_init_a(s_pfull + 8 * i, 128);
+        for (int i = 0; i < 2; i++) { mbar_init_a(s_hfull + 8 * i, 1); mbar_init_a(s_hfree + 8 * i, NCW); }
+        mbar_init_a(s_yfull, 1);
+        fence_mbar_init();
+        // transaction barriers are armed by their owner one phase ahead: the tail expects 2 KB per h tile, the chain 128 B of indices
+        if (is_chain) mbar_expect_a(s_yfull, 2 * TU * 4);
+        else { mbar_expect_a(s_hfull, 2048); mbar_expect_a(s_hfull + 8, 2048); }
+    }
+    if (tid < TU) {
+        const int b = tile * TU + tid;
+        ys[tid] = b < B ? p.yCur[b] : 128;
+        ys[TU + tid] = b < B ? p.yPrev[b] : 128;
+    }
+    if (is_chain) {
+        int* dil = reinterpret_cast<int*>(smem_raw + M::C_DIL);
+        if (tid == 0) { int d = 1; for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; } }
+        const uint32_t* ec = static_cast<const uint32_t*>(p.embCur);
+        for (int i = tid; i < A * 32; i += NTC) sts32(sm + M::C_EMB + ((i >> 5) * EROW + (i & 31)) * 4, ec[i]);
+    } else {
+        float* s_bout = reinterpret_cast<float*>(smem_raw + M::T_BOUT);
+        for (int i = tid; i < S; i += NTC) s_bout[i] = gbias[im.b_skpre + (size_t)(L - 1) * S + i];
+        for (int i = tid; i < A; i += NTC) { s_bout[S + i] = gbias[im.b_bzs + i]; s_bout[S + A + i] = gbias[im.b_bza + i]; }
+    }
+    __syncthreads();
+    cluster_sync_all();                                    // both CTAs' barriers are initialised before anybody signals the peer
+
+    const int w = warp, g = lane >> 2, t4 = lane & 3;
+    const int b0 = tile * TU + g, b1 = b0 + 8;
+    const bool v0 = b0 < B, v1 = b1 < B;
+    const uint32_t lane16 = (uint32_t)lane * 16;
+    const int jw = w >> 1, hw = w & 1;
+    const uint32_t xchg = (uint32_t)(jw * 512 + hw * 8) + lane16;
+    auto release = [&](uint32_t bar) { __syncwarp(); if (lane == 0) mbar_arrive_a(bar); };
+    auto release_remote = [&](uint32_t local_bar) { __syncwarp(); if (lane == 0) mbar_arrive_remote(mapa_u32(local_bar, peer)); };
+
+    if (is_chain) {
+        // ===================================================================================== chain CTA
+        if (warp == NCW) {
+            if (lane == 0) {
+                uint32_t pc = 0;
+                for (int t = t_begin; t < t_end; t++)
+                    for (int l = 0; l < L; l++, pc++) {
+                        const uint32_t sl = pc & 1;
+                        mbar_wait_a(s_empty + 8 * sl, ((pc >> 1) & 1) ^ 1);
+                        mbar_expect_a(s_full + 8 * sl, M::PIECE0);
+                        tma_load_a(sm + M::C_RING + sl * M::PIECE0, img + (size_t)l * im.layer_bytes, M::PIECE0, s_full + 8 * sl);
+                    }
+            }
+        } else {
+            int* dil = reinterpret_cast<int*>(smem_raw + M::C_DIL);
+            const uint32_t cstride = (uint32_t)ntiles_alloc * 4096u, rstride = (uint32_t)ntiles_alloc * 2048u;
+            const unsigned char* gcond = static_cast<const unsigned char*>(p.Lh) + (size_t)tile * 4096 + (size_t)(w * 32 + lane) * 16;
+            unsigned char* gring = static_cast<unsigned char*>(p.ring) + (size_t)tile * 2048;
+            const float* gbl = gbias + im.b_layer + (size_t)(w * 4 + t4) * 8;
+            const int cw = 8 * w + 2 * t4;
+            const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16, o_res = 32768u + (uint32_t)(w * 2) * 512 + lane16;
+            const uint32_t r_hbuf = mapa_u32(sm + M::T_HBUF + xchg, 1);            // this thread's slot of the tail CTA's h tiles
+            const uint32_t r_hfull = mapa_u32(s_hfull, 1);
+            auto advance = [&](StepIt& it) { if (++it.l == L) { it.l = 0; it.t++; if (++it.slot == slots) it.slot = 0; } };
+            StepIt itp{t_begin, 0, t_begin % slots};
+            uint32_t pcnt = 0;
+            auto stage_history = [&]() {
+                if (w < 4) {
+                    const uint32_t slot3 = pcnt % 3;
+                    const int d = dil[itp.l];
+                    const uint32_t dst = sm + M::C_PST + slot3 * 2048 + (uint32_t)(w * 32 + lane) * 16;
+                    if (itp.t >= t_end || itp.t < d) {
+                        sts128(dst, make_uint4(0, 0, 0, 0));
+                        mbar_arrive_a(s_pfull + 8 * slot3);
+                    } else {
+                        int sl = itp.slot - d; if (sl < 0) sl += slots;
+                        cp_async16(dst, gring + (size_t)((uint32_t)(sl * L + itp.l) * rstride) + (size_t)(w * 32 + lane) * 16);
+                        cp_async_arrive_noinc(s_pfull + 8 * slot3);
+                    }
+                }
+                pcnt++;
+                advance(itp);
+            };
+            uint32_t xa[4][4];
+            uint4 cbA = make_uint4(0, 0, 0, 0), cbB = make_uint4(0, 0, 0, 0);
+            float accp[2][4];
+            float2 brn, br_next;
+            float4 bh_next;
+            float xres[4] = {0.f, 0.f, 0.f, 0.f};
+            const unsigned char* cptr = gcond + (size_t)t_begin * L * cstride;
+            StepIt it1{0, 0, 0}, it3{0, 0, 0};
+            uint32_t pn = 0, kp = 0;
+            auto prep = [&](const uint32_t p1, const bool from_global, const bool pf_ok) {
+                brn = br_next;
+                const uint4 cb = kp ? cbA : cbB;
+                {
+                    const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
+                    accp[0][0] = bh_next.x + c0.x; accp[0][1] = bh_next.y + c0.y; accp[0][2] = bh_next.x + c1.x; accp[0][3] = bh_next.y + c1.y;
+                    accp[1][0] = bh_next.z + c2.x; accp[1][1] = bh_next.w + c2.y; accp[1][2] = bh_next.z + c3.x; accp[1][3] = bh_next.w + c3.y;
+                }
+                const uint32_t slot3 = pn % 3;
+                if (it1.t < t_end) {
+                    uint4 bt0, bg0, bt1, bg1;
+                    if (from_global) {
+                        const unsigned char* gp = img + (size_t)(L - 1) * im.layer_bytes + C::W_PREV;
+                        bt0 = ldg_nc_v4(gp + o_t0); bg0 = ldg_nc_v4(gp + o_g0); bt1 = ldg_nc_v4(gp + o_t0 + 512); bg1 = ldg_nc_v4(gp + o_g0 + 512);
+                    } else {
+                        bt0 = lds128(p1 + C::W_PREV + o_t0); bg0 = lds128(p1 + C::W_PREV + o_g0);
+                        bt1 = lds128(p1 + C::W_PREV + o_t0 + 512); bg1 = lds128(p1 + C::W_PREV + o_g0 + 512);
+                    }
+                    if (!pf_ok) mbar_wait_a(s_pfull + 8 * slot3, (pn / 3) & 1);
+                    uint32_t pb[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) load_a(pb[j], sm + M::C_PST + slot3 * 2048 + j * 512 + lane16);
+                    float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
+                    hmma(accp[0], pb[0], bt0.x, bt0.y); hmma(accp[1], pb[0], bg0.x, bg0.y); hmma(u0, pb[2], bt1.x, bt1.y); hmma(u1, pb[2], bg1.x, bg1.y);
+                    hmma(accp[0], pb[1], bt0.z, bt0.w); hmma(accp[1], pb[1], bg0.z, bg0.w); hmma(u0, pb[3], bt1.z, bt1.w); hmma(u1, pb[3], bg1.z, bg1.w);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
+                }
+                pn++;
+                {
+                    const unsigned char* src = cptr;
+                    cptr += cstride;
+                    const bool live = it3.t < t_end;
+                    ldg_nc_v4_if(cbA, src, live && kp != 0);
+                    ldg_nc_v4_if(cbB, src, live && kp == 0);
+                }
+                advance(it1); advance(it3);
+                bh_next = *reinterpret_cast<const float4*>(gbl + it1.l * 256);
+                br_next = *reinterpret_cast<const float2*>(gbl + it1.l * 256 + 4);
+            };
+            {   // prologue
+                const uint32_t* ep = static_cast<const uint32_t*>(p.embPrev);
+                sts32(sm + M::C_EPBUF + (g * EROW + 4 * w + t4) * 4, ep[ys[TU + g] * 32 + 4 * w + t4]);
+                sts32(sm + M::C_EPBUF + ((g + 8) * EROW + 4 * w + t4) * 4, ep[ys[TU + g + 8] * 32 + 4 * w + t4]);
+            }
+            StepIt it0{t_begin, 0, t_begin % slots};
+            stage_history(); stage_history(); stage_history();
+            {
+                it1 = it0; it3 = it0;
+                kp = 1;
+                cbA = ldg_nc_v4(cptr); cptr += cstride;
+                { StepIt i1 = it0; advance(i1); cbB = i1.t < t_end ? ldg_nc_v4(cptr) : make_uint4(0, 0, 0, 0); cptr += cstride; }
+                advance(it3); advance(it3);
+                bh_next = *reinterpret_cast<const float4*>(gbl); br_next = *reinterpret_cast<const float2*>(gbl + 4);
+                prep(0, true, false);
+                kp = 0;
+            }
+            bar_compute();
+
+            uint32_t pc = 0, epar = 0, hcnt = 0;               // ring piece counter, sample parity, h tiles handed over
+            bool ok_f = false, ok_pf = false, ok_hf = false;
+            for (int t = t_begin; t < t_end; t++) {
+                if (t > t_begin) {                             // the tail CTA has written this sample's indices into ys
+                    mbar_wait_a(s_yfull, (uint32_t)(t - t_begin - 1) & 1);
+                    if (tid == 0 && t + 1 < t_end) mbar_expect_a(s_yfull, 2 * TU * 4);          // arm the next hand-back
+                }
+                {   // embedding (reference.cpp:42-57), this warp's 8 channels
+                    const int yc0 = ys[g], yc1 = ys[g + 8];
+                    const uint32_t eo = sm + M::C_EPBUF + epar * (TU * EROW * 4);
+                    const float2 a0 = unpack_h2(lds32(eo + (g * EROW + 4 * w + t4) * 4)), a1 = unpack_h2(lds32(eo + ((g + 8) * EROW + 4 * w + t4) * 4));
+                    const float2 c0 = unpack_h2(lds32(sm + M::C_EMB + (yc0 * EROW + 4 * w + t4) * 4)), c1 = unpack_h2(lds32(sm + M::C_EMB + (yc1 * EROW + 4 * w + t4) * 4));
+                    xres[0] = a0.x + c0.x; xres[1] = a0.y + c0.y; xres[2] = a1.x + c1.x; xres[3] = a1.y + c1.y;
+                    if (p.tanhEmbed) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) xres[i] = wn::tanhf_fast(xres[i]);
+                    }
+                    const uint32_t x01 = pack_h2(xres[0], xres[1]), x23 = pack_h2(xres[2], xres[3]);
+                    sts64(sm + M::C_XBUF + xchg, x01, x23);
+                    stg_v2(gring + lane16 + (size_t)((uint32_t)(it0.slot * L) * rstride) + jw * 512 + hw * 8, x01, x23);
+                    const unsigned char* ep = static_cast<const unsigned char*>(p.embPrev);
+                    const uint32_t en = sm + M::C_EPBUF + (epar ^ 1) * (TU * EROW * 4);
+                    cp_async4(en + (g * EROW + 4 * w + t4) * 4, ep + (size_t)yc0 * 128 + (4 * w + t4) * 4);
+                    cp_async4(en + ((g + 8) * EROW + 4 * w + t4) * 4, ep + (size_t)yc1 * 128 + (4 * w + t4) * 4);
+                    cp_async_commit();
+                }
+                bar_compute();
+#pragma unroll
+                for (int j = 0; j < 4; j++) load_a(xa[j], sm + M::C_XBUF + j * 512 + lane16);
+
+                for (int l = 0; l < L; l++, pc++) {
+                    const uint32_t sl = pc & 1, p1 = sm + M::C_RING + sl * M::PIECE0, fph = (pc >> 1) & 1;
+                    const float2 br = brn;
+                    if (!ok_f) mbar_wait_a(s_full + 8 * sl, fph);
+                    {
+                        const uint4 bt0 = lds128(p1 + o_t0), bg0 = lds128(p1 + o_g0), bt1 = lds128(p1 + o_t0 + 512), bg1 = lds128(p1 + o_g0 + 512);
+                        float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
+                        hmma(accp[0], xa[0], bt0.x, bt0.y); hmma(accp[1], xa[0], bg0.x, bg0.y); hmma(u0, xa[2], bt1.x, bt1.y); hmma(u1, xa[2], bg1.x, bg1.y);
+                        hmma(accp[0], xa[1], bt0.z, bt0.w); hmma(accp[1], xa[1], bg0.z, bg0.w); hmma(u0, xa[3], bt1.z, bt1.w); hmma(u1, xa[3], bg1.z, bg1.w);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
+                    }
+                    {
+                        const __half2 half = __floats2half2_rn(0.5f, 0.5f);
+                        const __half2 tg0 = wn::tanh_h2(h2(pack_h2(accp[0][0], accp[0][1]))), tg1 = wn::tanh_h2(h2(pack_h2(accp[0][2], accp[0][3])));
+                        const __half2 sg0 = __hfma2(wn::tanh_h2(h2(pack_h2(0.5f * accp[1][0], 0.5f * accp[1][1]))), half, half);
+                        const __half2 sg1 = __hfma2(wn::tanh_h2(h2(pack_h2(0.5f * accp[1][2], 0.5f * accp[1][3]))), half, half);
+                        const uint32_t h01 = u32(__hmul2(tg0, sg0)), h23 = u32(__hmul2(tg1, sg1));
+                        sts64(sm + M::C_HBUF + xchg, h01, h23);
+                        // the tail CTA's copy: buffer hcnt & 1, free once the tail has read the tile of two steps ago
+                        if (!ok_hf) mbar_wait_a(s_hfree + 8 * (hcnt & 1), ((hcnt >> 1) & 1) ^ 1);
+                        st_async_v2(r_hbuf + (hcnt & 1) * 2048, h01, h23, r_hfull + 8 * (hcnt & 1));
+                        hcnt++;
+                    }
+                    prep(p1, false, ok_pf);
+                    bar_compute();
+                    uint32_t ha[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) load_a(ha[j], sm + M::C_HBUF + j * 512 + lane16);
+                    float ra[4] = {0.f, 0.f, 0.f, 0.f}, rb[4] = {0.f, 0.f, 0.f, 0.f};
+                    {
+                        const uint4 bw0 = lds128(p1 + o_res), bw1 = lds128(p1 + o_res + 512);
+                        hmma(ra, ha[0], bw0.x, bw0.y); hmma(rb, ha[2], bw1.x, bw1.y);
+                        hmma(ra, ha[1], bw0.z, bw0.w); hmma(rb, ha[3], bw1.z, bw1.w);
+                    }
+                    release(s_empty + 8 * sl);
+                    xres[0] = ((ra[0] + rb[0]) + br.x) + xres[0]; xres[1] = ((ra[1] + rb[1]) + br.y) + xres[1];
+                    xres[2] = ((ra[2] + rb[2]) + br.x) + xres[2]; xres[3] = ((ra[3] + rb[3]) + br.y) + xres[3];
+                    if (l + 1 < L) {
+                        const uint32_t x01 = pack_h2(xres[0], xres[1]), x23 = pack_h2(xres[2], xres[3]);
+                        sts64(sm + M::C_XBUF + xchg, x01, x23);
+                        stg_v2(gring + lane16 + (size_t)((uint32_t)(it0.slot * L + l + 1) * rstride) + jw * 512 + hw * 8, x01, x23);
+                    }
+                    if (DUMP) {
+                        if (v0) { p.xtOut[((size_t)l * B + b0) * R + cw] = xres[0]; p.xtOut[((size_t)l * B + b0) * R + cw + 1] = xres[1]; }
+                        if (v1) { p.xtOut[((size_t)l * B + b1) * R + cw] = xres[2]; p.xtOut[((size_t)l * B + b1) * R + cw + 1] = xres[3]; }
+                    }
+                    stage_history();
+                    {   // look at the coming step's barriers
+                        const uint32_t npc = pc + 1;
+                        ok_f = mbar_try_a(s_full + 8 * (npc & 1), (npc >> 1) & 1);
+                        ok_pf = mbar_try_a(s_pfull + 8 * (pn % 3), (pn / 3) & 1);
+                        ok_hf = mbar_try_a(s_hfree + 8 * (hcnt & 1), ((hcnt >> 1) & 1) ^ 1);
+                    }
+                    if (l + 1 < L) {
+                        bar_compute();
+#pragma unroll
+                        for (int j = 0; j < 4; j++) load_a(xa[j], sm + M::C_XBUF + j * 512 + lane16);
+                    }
+                    kp ^= 1;
+                }
+                cp_async_wait_all();
+                epar ^= 1;
+                if (++it0.slot == slots) it0.slot = 0;
+                it0.t++;
+            }
+        }
+    } else {
+        // ===================================================================================== tail CTA
+        if (warp == NCW) {
+            if (lane == 0) {
+                uint32_t pc = 0;
+                auto put = [&](const unsigned char* src, uint32_t bytes) {
+                    const uint32_t sl = pc & 3;
+                    mbar_wait_a(s_empty + 8 * sl, ((pc >> 2) & 1) ^ 1);
+                    mbar_expect_a(s_full + 8 * sl, bytes);
+                    tma_load_a(sm + M::T_RING + sl * M::SLOT1, src, bytes, s_full + 8 * sl);
+                    pc++;
+                };
+                for (int t = t_begin; t < t_end; t++) {
+                    for (int l = 0; l < L; l++) put(img + (size_t)l * im.layer_bytes + C::W_SKIP, S * 128);
+                    for (int q = 0; q < NQ; q++)
+                        put(q < C::NQ_ZS ? img + im.off_zs + (size_t)q * C::ZS_PIECE : img + im.off_za + (size_t)(q - C::NQ_ZS) * C::ZA_PIECE,
+                            q < C::NQ_ZS ? C::ZS_PIECE : C::ZA_PIECE);
+                }
+            }
+        } else {
+            float* s_bout = reinterpret_cast<float*>(smem_raw + M::T_BOUT);
+            const uint32_t o_skip = (uint32_t)(w * C::NSK * 2) * 512 + lane16, o_out = (uint32_t)(4 * w) * 512;
+            float sk[C::NSK][4];
+#pragma unroll
+            for (int i = 0; i < C::NSK; i++) sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
+            uint32_t pc = 0, hcnt = 0;
+            for (int t = t_begin; t < t_end; t++) {
+                const float sel0 = (2 * w + 0 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w] : 0.5f;
+                const float sel1 = (2 * w + 1 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w + 1] : 0.5f;
+                for (int l = 0; l < L; l++, pc++, hcnt++) {
+                    const uint32_t hb = sm + M::T_HBUF + (hcnt & 1) * 2048;
+                    mbar_wait_a(s_hfull + 8 * (hcnt & 1), (hcnt >> 1) & 1);
+                    uint32_t ha[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) load_a(ha[j], hb + j * 512 + lane16);
+                    const uint32_t sl = pc & 3, p2 = sm + M::T_RING + sl * M::SLOT1;
+                    mbar_wait_a(s_full + 8 * sl, (pc >> 2) & 1);
+#pragma unroll
+                    for (int jp = 0; jp < 2; jp++) {
+                        uint4 bw[C::NSK];
+#pragma unroll
+                        for (int i = 0; i < C::NSK; i++) bw[i] = lds128(p2 + o_skip + (i * 2 + jp) * 512);
+#pragma unroll
+                        for (int i = 0; i < C::NSK; i++) hmma(sk[i], ha[2 * jp], bw[i].x, bw[i].y);
+#pragma unroll
+                        for (int i = 0; i < C::NSK; i++) hmma(sk[i], ha[2 * jp + 1], bw[i].z, bw[i].w);
+                    }
+                    // the h tile has been read (the HMMAs above hold its values): arm its barrier for the tile after next (one thread,
+                    // ordered before this warp's "free" signal), then hand the buffer back to the chain CTA
+                    if (tid == 0) mbar_expect_a(s_hfull + 8 * (hcnt & 1), 2048);
+                    release_remote(s_hfree + 8 * (hcnt & 1));
+                    release(s_empty + 8 * sl);
+                    if (DUMP) {
+                        const float* pre = gbias + im.b_skpre + (size_t)l * S;
+#pragma unroll
+                        for (int i = 0; i < C::NSK; i++) {
+                            const int c = 8 * (w * C::NSK + i) + 2 * t4;
+                            float o0 = sk[i][0] + pre[c], o1 = sk[i][1] + pre[c + 1], o2 = sk[i][2] + pre[c], o3 = sk[i][3] + pre[c + 1];
+                            if (l == L - 1) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
+                            if (v0) { p.skipOut[((size_t)l * B + b0) * S + c] = o0; p.skipOut[((size_t)l * B + b0) * S + c + 1] = o1; }
+                            if (v1) { p.skipOut[((size_t)l * B + b1) * S + c] = o2; p.skipOut[((size_t)l * B + b1) * S + c + 1] = o3; }
+                        }
+                    }
+                }
+                // ---------------- relu(skip + bias) -> Zs -> Za   (reference.cpp:93-104)
+#pragma unroll
+                for (int i = 0; i < C::NSK; i++) {
+                    const int nt = w * C::NSK + i, c = 8 * nt + 2 * t4;
+                    const float b0f = s_bout[c], b1f = s_bout[c + 1];
+                    sts64(sm + M::T_OB0 + (nt >> 1) * 512 + lane16 + (nt & 1) * 8,
+                          pack_h2(fmaxf(sk[i][0] + b0f, 0.f), fmaxf(sk[i][1] + b1f, 0.f)), pack_h2(fmaxf(sk[i][2] + b0f, 0.f), fmaxf(sk[i][3] + b1f, 0.f)));
+                    sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
+                }
+                bar_compute();
+                float zz[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int c = 32 * w + 8 * i + 2 * t4;
+                    zz[i][0] = zz[i][2] = s_bout[S + c]; zz[i][1] = zz[i][3] = s_bout[S + c + 1];
+                }
+                auto out_gemm = [&](const int ojp, const uint32_t abuf, const int kp0) {
+                    const uint32_t sl = pc & 3, st = sm + M::T_RING + sl * M::SLOT1 + o_out * ojp + lane16;
+                    mbar_wait_a(s_full + 8 * sl, (pc >> 2) & 1);
+                    for (int jp = 0; jp < ojp; jp++) {
+                        uint32_t a0[4], a1[4];
+                        load_a(a0, abuf + ((kp0 + jp) * 2) * 512 + lane16);
+                        load_a(a1, abuf + ((kp0 + jp) * 2 + 1) * 512 + lane16);
+                        uint4 bw[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) bw[i] = lds128(st + (i * ojp + jp) * 512);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) hmma(zz[i], a0, bw[i].x, bw[i].y);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) hmma(zz[i], a1, bw[i].z, bw[i].w);
+                    }
+                    release(s_empty + 8 * sl);
+                    pc++;
+                };
+#pragma unroll
+                for (int q = 0; q < C::NQ_ZS; q++) out_gemm(C::OJP_ZS, sm + M::T_OB0, q * C::OJP_ZS);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int nt = 4 * w + i, c = 8 * nt + 2 * t4;
+                    const float z0 = fmaxf(zz[i][0], 0.f), z1 = fmaxf(zz[i][1], 0.f), z2 = fmaxf(zz[i][2], 0.f), z3 = fmaxf(zz[i][3], 0.f);
+                    sts64(sm + M::T_OB1 + (nt >> 1) * 512 + lane16 + (nt & 1) * 8, pack_h2(z0, z1), pack_h2(z2, z3));
+                    if (DUMP) {
+                        if (v0) { p.Zs[(size_t)b0 * A + c] = z0; p.Zs[(size_t)b0 * A + c + 1] = z1; }
+                        if (v1) { p.Zs[(size_t)b1 * A + c] = z2; p.Zs[(size_t)b1 * A + c + 1] = z3; }
+                    }
+                    zz[i][0] = zz[i][2] = s_bout[S + A + c]; zz[i][1] = zz[i][3] = s_bout[S + A + c + 1];
+                }
+                bar_compute();
+#pragma unroll
+                for (int q = 0; q < C::NQ_ZA; q++) out_gemm(C::OJP_ZA, sm + M::T_OB1, q * C::OJP_ZA);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int c = 32 * w + 8 * i + 2 * t4;
+                    sts64(sm + M::T_LBUF + (g * LROW + c) * 4, __float_as_uint(zz[i][0]), __float_as_uint(zz[i][1]));
+                    sts64(sm + M::T_LBUF + ((g + 8) * LROW + c) * 4, __float_as_uint(zz[i][2]), __float_as_uint(zz[i][3]));
+                    if (DUMP) {
+                        if (v0) { p.Za[(size_t)b0 * A + c] = zz[i][0]; p.Za[(size_t)b0 * A + c + 1] = zz[i][1]; }
+                        if (v1) { p.Za[(size_t)b1 * A + c] = zz[i][2]; p.Za[(size_t)b1 * A + c + 1] = zz[i][3]; }
+                    }
+                }
+                bar_compute();
+                {   // softmax + categorical sample: warp w serves utterances 2w and 2w+1; lane holds 8 consecutive classes of each
+                    float e[2][8], m[2] = {0.f, 0.f};
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const uint4 u0 = lds128(sm + M::T_LBUF + ((2 * w + r) * LROW + 8 * lane) * 4), u1 = lds128(sm + M::T_LBUF + ((2 * w + r) * LROW + 8 * lane + 4) * 4);
+                        e[r][0] = __uint_as_float(u0.x); e[r][1] = __uint_as_float(u0.y); e[r][2] = __uint_as_float(u0.z); e[r][3] = __uint_as_float(u0.w);
+                        e[r][4] = __uint_as_float(u1.x); e[r][5] = __uint_as_float(u1.y); e[r][6] = __uint_as_float(u1.z); e[r][7] = __uint_as_float(u1.w);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) m[r] = fmaxf(m[r], e[r][k]);
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        m[0] = fmaxf(m[0], __shfl_xor_sync(0xffffffffu, m[0], o));
+                        m[1] = fmaxf(m[1], __shfl_xor_sync(0xffffffffu, m[1], o));
+                    }
+                    float incl[2];
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const float ms = m[r] * 1.4426950408889634f;
+                        float run = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) { run += wn::exp2f_fast(fmaf(e[r][k], 1.4426950408889634f, -ms)); e[r][k] = run; }
+                        incl[r] = run;
+                    }
+                    const float tot_lane[2] = {incl[0], incl[1]};
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float a0 = __shfl_up_sync(0xffffffffu, incl[0], o), a1 = __shfl_up_sync(0xffffffffu, incl[1], o);
+                        if (lane >= o) { incl[0] += a0; incl[1] += a1; }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const float total = __shfl_sync(0xffffffffu, incl[r], 31);
+                        const float excl = incl[r] - tot_lane[r];
+                        const float target = (r == 0 ? sel0 : sel1) * total;
+                        int cntk = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) cntk += (target < excl + e[r][k]) ? 0 : 1;
+                        const unsigned ball = __ballot_sync(0xffffffffu, target < incl[r]);
+                        const int lf = ball ? __ffs(ball) - 1 : 31;
+                        const int ck = __shfl_sync(0xffffffffu, cntk, lf);
+                        const int y = ball ? 8 * lf + (ck < 7 ? ck : 7) : A - 1;
+                        const int b = tile * TU + 2 * w + r;
+                        if (DUMP && b < B) {
+                            const float inv = 1.f / total;
+                            float prevv = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 8; k++) { p.P[(size_t)b * A + 8 * lane + k] = (e[r][k] - prevv) * inv; prevv = e[r][k]; }
+                        }
+                        if (lane == 0) {
+                            int fbk = y;
+                            if (b < B) {
+                                p.yOut[(size_t)b * p.N + t] = y;
+                                if (p.forced) fbk = p.forced[(size_t)b * p.N + t];
+                            } else fbk = 128;
+                            const int yold = ys[2 * w + r];
+                            ys[TU + 2 * w + r] = yold;
+                            ys[2 * w + r] = fbk;
+                            // the chain CTA's copy (it reads it after waiting for yfull)
+                            if (t + 1 < t_end) {                  // the chain CTA's copy: data + completion on its yfull barrier
+                                const uint32_t rb = mapa_u32(s_yfull, 0);
+                                st_async_u32(mapa_u32(sm + M::O_YS + (TU + 2 * w + r) * 4, 0), (uint32_t)yold, rb);
+                                st_async_u32(mapa_u32(sm + M::O_YS + (2 * w + r) * 4, 0), (uint32_t)fbk, rb);
+                            }
+                        }
+                    }
+                }
+                bar_compute();
+            }
+            if (tid < TU && tile * TU + tid < B) { p.yCur[tile * TU + tid] = ys[tid]; p.yPrev[tile * TU + tid] = ys[TU + tid]; }
+        }
+    }
+    // nobody leaves while the peer may still write into this CTA's shared memory or arrive on its barriers
+    cluster_sync_all();
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -883,12 +1429,53 @@ static cudaError_t lat_launch_S(const WnParams& p, const unsigned char* im8, int
     return cudaSuccess;
 }
 
-cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, cudaStream_t stream, WnLaunchInfo* info)
+// the two-CTA cluster variant: grid = 2 x tiles, cluster (2, 1, 1)
+template <int S, bool DUMP>
+static cudaError_t lat2_go(const WnParams& pp, const unsigned char* im8, int tiles, int ntiles_alloc, cudaStream_t stream)
+{
+    const size_t smem = CfgC<S>::SMEM;
+    cudaError_t e = cudaFuncSetAttribute(wn_lat2_kernel<S, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * tiles, 1, 1);
+    cfg.blockDim = dim3(NTC, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, wn_lat2_kernel<S, DUMP>, pp, im8, ntiles_alloc);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+template <int S>
+static cudaError_t lat2_launch_S(const WnParams& p, const unsigned char* im8, int tiles, int ntiles_alloc, cudaStream_t stream, size_t* smem_out)
+{
+    *smem_out = CfgC<S>::SMEM;
+    WnParams head = p, tail = p;
+    if (p.dump) { head.count = p.count - 1; head.dump = 0; tail.init_sample = p.init_sample + p.count - 1; tail.count = 1; }
+    cudaError_t e = cudaSuccess;
+    if (head.count > 0) e = lat2_go<S, false>(head, im8, tiles, ntiles_alloc, stream);
+    if (e == cudaSuccess && p.dump) e = lat2_go<S, true>(tail, im8, tiles, ntiles_alloc, stream);
+    return e;
+}
+
+// cluster: serve every 16-utterance tile with a cluster of two CTAs (chain / tail) instead of one
+cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, bool cluster, cudaStream_t stream, WnLaunchInfo* info)
 {
     const int grid = wn_lat_tiles(p.B), ntiles_alloc = wn_lat_tiles(engine_B);
     const unsigned char* im8 = static_cast<const unsigned char*>(image);
     size_t smem = 0;
     cudaError_t e;
+    if (cluster && !p.trace) {
+        if (p.S == 256) e = lat2_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);
+        else if (p.S == 128) e = lat2_launch_S<128>(p, im8, grid, ntiles_alloc, stream, &smem);
+        else return cudaErrorInvalidValue;
+        if (e != cudaSuccess) return e;
+        if (info) { info->kernel = 18; info->grid = 2 * grid; info->block = NTC; info->smem_bytes = (int)smem; info->batch_per_cta = TU; info->cluster = 2; }
+        return cudaGetLastError();
+    }
     if (p.S == 256) e = lat_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);
     else if (p.S == 128) e = lat_launch_S<128>(p, im8, grid, ntiles_alloc, stream, &smem);
     else return cudaErrorInvalidValue;

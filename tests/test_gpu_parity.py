@@ -202,17 +202,19 @@ def _logit_check(za_o, za_g, rel=1e-2, mean_rel=None):
         assert (err / scale).mean() <= mean_rel, f"mean err / scale {(err / scale).mean()}"
 
 
-FP16_KERNELS = ["stream", "lat", "tc", "tc_tile32_fused", "tc_tile64_fused", "tc_nodup"]
+FP16_KERNELS = ["stream", "lat", "lat_single", "tc", "tc_tile32_fused", "tc_tile64_fused", "tc_nodup"]
 
 
 def _select_fp16_kernel(kernel, monkeypatch):
     """Environment switches read once by nvwn_create: which fp16 kernel, and which tile shape / schedule of the tensor-core one."""
-    for k in ("NVWN_FP16_KERNEL", "NVWN_TC_TILE", "NVWN_TC_NODUP", "NVWN_TC_FUSED"):
+    for k in ("NVWN_FP16_KERNEL", "NVWN_TC_TILE", "NVWN_TC_NODUP", "NVWN_TC_FUSED", "NVWN_LAT_CLUSTER"):
         monkeypatch.delenv(k, raising=False)
     if kernel == "stream":
         monkeypatch.setenv("NVWN_FP16_KERNEL", "stream")
-    elif kernel == "lat":                          # latency-mode kernel (mma.sync, 16-utterance tiles): what AUTO picks up to 2368 utterances
+    elif kernel == "lat":                          # latency-mode kernel (mma.sync, 16-utterance tiles, a two-CTA cluster per tile): AUTO up to 1184 utterances
         monkeypatch.setenv("NVWN_FP16_KERNEL", "lat")
+    elif kernel == "lat_single":                   # ... one CTA per tile: what AUTO uses from 1185 to 2368 utterances
+        monkeypatch.setenv("NVWN_FP16_KERNEL", "lat"); monkeypatch.setenv("NVWN_LAT_CLUSTER", "0")
     else:                                          # tensor-core (tcgen05) kernel; "tc" = the auto-selected 64-utterance tiles, unfused schedule
         monkeypatch.setenv("NVWN_FP16_KERNEL", "tc")
         if kernel == "tc_nodup":                   # 128-utterance tiles, two threads per utterance (debug variant, see wn_tc_tile_utt)
@@ -257,7 +259,9 @@ def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
         e.set_forced(f)
         y = np.zeros((B, n_run), np.int32)
         e.run(n_run, B, y, dump_activations=True); e.synchronize()
-        assert e.launch_info()["kernel"] == {"stream": 16, "lat": 18}.get(kernel, 17)
+        assert e.launch_info()["kernel"] == {"stream": 16, "lat": 18, "lat_single": 18}.get(kernel, 17)
+        if kernel.startswith("lat"):
+            assert e.launch_info()["cluster"] == (2 if kernel == "lat" else 1)
         o16 = cpu_oracle(wn_, L, B, n_run, R, S, A, md, prec=po.PREC_FP16); o16.set_forced(f); o16.run(n_run, B)
         o = cpu_oracle(wn_, L, B, n_run, R, S, A, md); o.set_forced(f); o.run(n_run, B)
         ag = e.activations()
@@ -266,7 +270,7 @@ def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
         assert np.allclose(ag["p"].sum(axis=1), 1.0, atol=1e-3)
         assert np.abs(ag["p"] - o.get_p()).max() <= 1e-2 * o.get_p().max()
         _check_sampled_index(ag["p"], wn_["selectors"][n_run - 1], y[:, n_run - 1])
-        if kernel == "lat":
+        if kernel.startswith("lat"):
             # intermediate activations of the last step against the fp16-contract oracle
             ao = o16.activations()
             for k, tol in (("xt", 2e-2), ("skip", 2e-2), ("zs", 2e-2)):
@@ -309,7 +313,7 @@ def _run_range(e, init, count, N, B, y=None):
     e._samples_per_chunk = 0
 
 
-@pytest.mark.parametrize("kernel", ["lat", "tc"])      # "tc" = what AUTO selects above the latency kernel's range: 64-utterance tiles, unfused schedule
+@pytest.mark.parametrize("kernel", ["lat", "lat_single", "tc"])      # "tc" = what AUTO selects above the latency kernels' range: 64-utterance tiles, unfused schedule
 def test_fp16_soak_determinism_and_chunking(kernel, monkeypatch):
     """The fp16 kernels at the C3 shape (L20 R64 S256 A256, maxDil 512, 64 utterances) over 2000 samples -- several turns of the
     513-slot history ring and of the dilation cycle: run twice -> identical yOut; run_chunks(97) and three unequal
@@ -333,7 +337,7 @@ def test_fp16_soak_determinism_and_chunking(kernel, monkeypatch):
     assert np.array_equal(y1, y4), "three unequal run_partial pieces != one launch"
 
 
-@pytest.mark.parametrize("kernel", ["lat", "tc"])
+@pytest.mark.parametrize("kernel", ["lat", "lat_single", "tc"])
 def test_fp16_logits_after_ring_wrap(kernel, monkeypatch):
     """Teacher-forced logits at step N-1 = 599 > maxDil + 1 = 513 (real ring wrap, every dilation live) against the oracle."""
     R, S, A, L, B, N, md = 64, 256, 256, 20, 16, 600, 512

@@ -9,6 +9,7 @@ import torch
 sys.path.insert(0, ".")
 import os
 os.environ.setdefault("NVWN_FP16_KERNEL", "lat")
+os.environ.setdefault("NVWN_LAT_CLUSTER", "0")          # the timeline instrumentation lives in the single-CTA kernel
 import nv_wavenet_b200 as nw
 from nv_wavenet_b200 import _lib
 from tests import refgen
