@@ -455,12 +455,12 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(prof):
         try:
             pj = json.load(open(prof))
-            if pj.get("config") == args.config and pj.get("kernel_id") == info["kernel"]:
+            if pj.get("config") == args.config and pj.get("kernel_id") == info["kernel"] and kname in pj.get("kernel", ""):
                 traffic_x = {"value": pj["dram_bytes_per_unit"] * B * N, "dram_bytes_per_unit": pj["dram_bytes_per_unit"],
                              "capture_samples": pj.get("capture_samples"), "capture_batch": pj.get("capture_batch"), "source": "profiles/ncu_summary.json"}
         except Exception:
             traffic_x = None
-    kname = {16: "wn_stream_kernel", 17: "wn_tc_kernel", 18: "wn_lat_kernel"}.get(info["kernel"], str(info["kernel"]))
+    kname = {16: "wn_stream_kernel", 17: "wn_tc_kernel", 18: "wn_lat2_kernel" if info["cluster"] == 2 else "wn_lat_kernel"}.get(info["kernel"], str(info["kernel"]))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "traffic_extrapolated": traffic_x, "peak_source": peak_src, "kernel": kname,
                 "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_unit": alg, "units_per_launch": B * N,
@@ -485,7 +485,7 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == nw.FP16 else "f32", "arithmetic": {nw.FP16: "fp16 inputs, fp32 accumulate", nw.FP32: "fp32, bit-exact to the reference CPU model", nw.FP32_FAST: "fp32, reference GPU kernels' order (FMA, 2 partial sums)"}[dtype],
         "data": "synthetic", "config": workload_config(args, world * B),
         "khz_per_utterance": N / (elapsed_ms / args.steps), "clocks": clk, "e2e": e2e, "gpu_launches": launches,
-        "launch": {k: info[k] for k in ("kernel", "grid", "block", "smem_bytes", "batch_per_cta")},
+        "launch": {k: info[k] for k in ("kernel", "grid", "block", "smem_bytes", "batch_per_cta", "cluster")},
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
     print(json.dumps(line), flush=True)
