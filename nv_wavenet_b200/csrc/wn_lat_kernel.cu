@@ -141,7 +141,6 @@ __device__ __forceinline__ void ldg_nc_v4_if(uint4& d, const void* p, bool pred)
                  : "+r"(d.x), "+r"(d.y), "+r"(d.z), "+r"(d.w) : "l"(p), "r"((uint32_t)pred) : "memory");
 }
 __device__ __forceinline__ void stg_v2(void* p, uint32_t a, uint32_t b) { asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory"); }
-__device__ __forceinline__ void stg_v4(void* p, uint4 v) { asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b)
 {
@@ -158,6 +157,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // mbarrier by shared-memory address
 __device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -167,12 +167,6 @@ __device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ bool mbar_test_a(uint32_t bar, uint32_t parity)      // non-blocking probe
-{
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
 // three looks issued back to back: their ~90-cycle latencies overlap
@@ -838,7 +832,9 @@ struct CfgC {
     static constexpr uint32_t C_XBUF = C_PST + 3 * 2048;
     static constexpr uint32_t C_HBUF = C_XBUF + 2048;
     static constexpr uint32_t C_DIL = C_HBUF + 2048;
-    static constexpr uint32_t C_END = C_DIL + MAXL * 4;
+    static constexpr uint32_t C_COND = C_DIL + MAXL * 4;                  // 4 x 4 KB: conditioning tiles, staged three steps ahead (cp.async)
+    static constexpr uint32_t C_BIAS = C_COND + 4 * 4096;                  // [L][8 warps][4][8] fp32: Bh / Bres pairs per thread
+    static constexpr uint32_t C_END = C_BIAS + MAXL * 1024;
     // tail CTA
     static constexpr uint32_t T_RING = 0;                                  // NSLOT1 x SLOT1
     static constexpr uint32_t T_BOUT = NSLOT1 * SLOT1;
@@ -859,8 +855,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v2(uint32_t raddr, uint32_t a, uint32_t b) { asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" ::"r"(raddr), "r"(a), "r"(b) : "memory"); }
-__device__ __forceinline__ void st_cluster_u32(uint32_t raddr, uint32_t a) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(a) : "memory"); }
 // remote stores that complete bytes on a remote mbarrier (data and signal travel together: no release fence on the sender)
 __device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t a, uint32_t b, uint32_t rbar)
 {
@@ -872,26 +866,19 @@ __device__ __forceinline__ void st_async_u32(uint32_t raddr, uint32_t a, uint32_
 }
 // "this buffer is free again": no data behind it, so no release ordering is paid for
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) { asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory"); }
-__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
-{
-    uint32_t spins = 0;
-    while (!mbar_try_cluster(bar, parity))
-        if (++spins > (1u << 24)) lat_timeout(bar, parity);
-}
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int S, bool DUMP>
+template <int S, bool DUMP, bool TRC>
 __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const unsigned char* __restrict__ img, const int ntiles_alloc)
 {
+    // debug timeline (tools/lat_trace.py): role 0 = chain CTA thread 0, role 1 = tail CTA thread 0, of the first cluster
+    unsigned long long* trc = (TRC && p.trace && blockIdx.x < 2) ? p.trace : nullptr;
+    int trn = 0;
+    const int tr_t = p.trace_t & 0xFFFF;
+#define TRACE2(role, tag) do { if (TRC && trc && threadIdx.x == 0 && t == tr_t && trn < 1023) trc[(role) * 1024 + trn++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
     using C = Cfg<S>;
     using M = CfgC<S>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -934,6 +921,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
         if (tid == 0) { int d = 1; for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; } }
         const uint32_t* ec = static_cast<const uint32_t*>(p.embCur);
         for (int i = tid; i < A * 32; i += NTC) sts32(sm + M::C_EMB + ((i >> 5) * EROW + (i & 31)) * 4, ec[i]);
+        for (int i = tid; i < L * 256; i += NTC) sts32(sm + M::C_BIAS + i * 4, __float_as_uint(gbias[im.b_layer + i]));
     } else {
         float* s_bout = reinterpret_cast<float*>(smem_raw + M::T_BOUT);
         for (int i = tid; i < S; i += NTC) s_bout[i] = gbias[im.b_skpre + (size_t)(L - 1) * S + i];
@@ -969,15 +957,24 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
             const uint32_t cstride = (uint32_t)ntiles_alloc * 4096u, rstride = (uint32_t)ntiles_alloc * 2048u;
             const unsigned char* gcond = static_cast<const unsigned char*>(p.Lh) + (size_t)tile * 4096 + (size_t)(w * 32 + lane) * 16;
             unsigned char* gring = static_cast<unsigned char*>(p.ring) + (size_t)tile * 2048;
-            const float* gbl = gbias + im.b_layer + (size_t)(w * 4 + t4) * 8;
             const int cw = 8 * w + 2 * t4;
             const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16, o_res = 32768u + (uint32_t)(w * 2) * 512 + lane16;
             const uint32_t r_hbuf = mapa_u32(sm + M::T_HBUF + xchg, 1);            // this thread's slot of the tail CTA's h tiles
             const uint32_t r_hfull = mapa_u32(s_hfull, 1);
+            const uint32_t s_bias = sm + M::C_BIAS + (uint32_t)(w * 4 + t4) * 32;   // this thread's Bh / Bres pairs of layer 0 (+ 1 KB per layer)
+            const uint32_t s_cond = sm + M::C_COND + (uint32_t)(w * 32 + lane) * 16;  // this thread's 16 B of a conditioning tile (+ 4 KB per slot)
             auto advance = [&](StepIt& it) { if (++it.l == L) { it.l = 0; it.t++; if (++it.slot == slots) it.slot = 0; } };
+            // Staging of the step `itp` (three steps ahead of its use), no register and no scoreboard involved:
+            //  * its conditioning tile: every thread copies the 16 bytes it will read back itself (cp.async; completion = the thread's
+            //    own cp.async group, no barrier) into a 4-slot ring;
+            //  * its dilated history x_l[t-d] (zero before the start of the utterance, nv_wavenet.cuh:106): warps 0-3, 128 x 16 B, into
+            //    a 3-slot ring, completion on an mbarrier (every warp reads the whole tile).
             StepIt itp{t_begin, 0, t_begin % slots};
             uint32_t pcnt = 0;
-            auto stage_history = [&]() {
+            const unsigned char* cptr = gcond + (size_t)t_begin * L * cstride;         // conditioning of step itp (steps are consecutive in memory)
+            auto stage_step = [&]() {
+                if (itp.t < t_end) cp_async16(s_cond + (pcnt & 3) * 4096, cptr);
+                cptr += cstride;
                 if (w < 4) {
                     const uint32_t slot3 = pcnt % 3;
                     const int d = dil[itp.l];
@@ -991,35 +988,39 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                         cp_async_arrive_noinc(s_pfull + 8 * slot3);
                     }
                 }
+                cp_async_commit();
                 pcnt++;
                 advance(itp);
             };
             uint32_t xa[4][4];
-            uint4 cbA = make_uint4(0, 0, 0, 0), cbB = make_uint4(0, 0, 0, 0);
             float accp[2][4];
-            float2 brn, br_next;
-            float4 bh_next;
+            float2 brn = make_float2(0.f, 0.f);
             float xres[4] = {0.f, 0.f, 0.f, 0.f};
-            const unsigned char* cptr = gcond + (size_t)t_begin * L * cstride;
-            StepIt it1{0, 0, 0}, it3{0, 0, 0};
-            uint32_t pn = 0, kp = 0;
+            StepIt it1{0, 0, 0};
+            uint32_t pn = 0;
+            // accp <- (Bh + Lh) + Wprev . x[t-d] of the coming step it1 (staged tile number pn); everything it reads is in shared memory
             auto prep = [&](const uint32_t p1, const bool from_global, const bool pf_ok) {
-                brn = br_next;
-                const uint4 cb = kp ? cbA : cbB;
-                {
-                    const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
-                    accp[0][0] = bh_next.x + c0.x; accp[0][1] = bh_next.y + c0.y; accp[0][2] = bh_next.x + c1.x; accp[0][3] = bh_next.y + c1.y;
-                    accp[1][0] = bh_next.z + c2.x; accp[1][1] = bh_next.w + c2.y; accp[1][2] = bh_next.z + c3.x; accp[1][3] = bh_next.w + c3.y;
-                }
                 const uint32_t slot3 = pn % 3;
                 if (it1.t < t_end) {
                     uint4 bt0, bg0, bt1, bg1;
                     if (from_global) {
                         const unsigned char* gp = img + (size_t)(L - 1) * im.layer_bytes + C::W_PREV;
                         bt0 = ldg_nc_v4(gp + o_t0); bg0 = ldg_nc_v4(gp + o_g0); bt1 = ldg_nc_v4(gp + o_t0 + 512); bg1 = ldg_nc_v4(gp + o_g0 + 512);
+                        cp_async_wait_all();
                     } else {
                         bt0 = lds128(p1 + C::W_PREV + o_t0); bg0 = lds128(p1 + C::W_PREV + o_g0);
                         bt1 = lds128(p1 + C::W_PREV + o_t0 + 512); bg1 = lds128(p1 + C::W_PREV + o_g0 + 512);
+                        cp_async_wait_pending<1>();            // this thread's conditioning of step it1 has landed (the group of the step after may be in flight)
+                    }
+                    const uint4 cb = lds128(s_cond + (pn & 3) * 4096);
+                    const uint4 bq = lds128(s_bias + it1.l * 1024);
+                    const uint4 b2 = lds128(s_bias + it1.l * 1024 + 16);
+                    const float4 bh = make_float4(__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z), __uint_as_float(bq.w));
+                    brn = make_float2(__uint_as_float(b2.x), __uint_as_float(b2.y));
+                    {
+                        const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
+                        accp[0][0] = bh.x + c0.x; accp[0][1] = bh.y + c0.y; accp[0][2] = bh.x + c1.x; accp[0][3] = bh.y + c1.y;
+                        accp[1][0] = bh.z + c2.x; accp[1][1] = bh.w + c2.y; accp[1][2] = bh.z + c3.x; accp[1][3] = bh.w + c3.y;
                     }
                     if (!pf_ok) mbar_wait_a(s_pfull + 8 * slot3, (pn / 3) & 1);
                     uint32_t pb[4][4];
@@ -1032,39 +1033,23 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
                 }
                 pn++;
-                {
-                    const unsigned char* src = cptr;
-                    cptr += cstride;
-                    const bool live = it3.t < t_end;
-                    ldg_nc_v4_if(cbA, src, live && kp != 0);
-                    ldg_nc_v4_if(cbB, src, live && kp == 0);
-                }
-                advance(it1); advance(it3);
-                bh_next = *reinterpret_cast<const float4*>(gbl + it1.l * 256);
-                br_next = *reinterpret_cast<const float2*>(gbl + it1.l * 256 + 4);
+                advance(it1);
             };
-            {   // prologue
+            {   // prologue: previous-index rows of the first sample; staging of steps 0, 1, 2; pre-activation of step 0
                 const uint32_t* ep = static_cast<const uint32_t*>(p.embPrev);
                 sts32(sm + M::C_EPBUF + (g * EROW + 4 * w + t4) * 4, ep[ys[TU + g] * 32 + 4 * w + t4]);
                 sts32(sm + M::C_EPBUF + ((g + 8) * EROW + 4 * w + t4) * 4, ep[ys[TU + g + 8] * 32 + 4 * w + t4]);
             }
             StepIt it0{t_begin, 0, t_begin % slots};
-            stage_history(); stage_history(); stage_history();
-            {
-                it1 = it0; it3 = it0;
-                kp = 1;
-                cbA = ldg_nc_v4(cptr); cptr += cstride;
-                { StepIt i1 = it0; advance(i1); cbB = i1.t < t_end ? ldg_nc_v4(cptr) : make_uint4(0, 0, 0, 0); cptr += cstride; }
-                advance(it3); advance(it3);
-                bh_next = *reinterpret_cast<const float4*>(gbl); br_next = *reinterpret_cast<const float2*>(gbl + 4);
-                prep(0, true, false);
-                kp = 0;
-            }
+            stage_step(); stage_step(); stage_step();
+            it1 = it0;
+            prep(0, true, false);                                       // leaves it1 = step 1
             bar_compute();
 
             uint32_t pc = 0, epar = 0, hcnt = 0;               // ring piece counter, sample parity, h tiles handed over
             bool ok_f = false, ok_pf = false, ok_hf = false;
             for (int t = t_begin; t < t_end; t++) {
+                TRACE2(0, 1);
                 if (t > t_begin) {                             // the tail CTA has written this sample's indices into ys
                     mbar_wait_a(s_yfull, (uint32_t)(t - t_begin - 1) & 1);
                     if (tid == 0 && t + 1 < t_end) mbar_expect_a(s_yfull, 2 * TU * 4);          // arm the next hand-back
@@ -1086,11 +1071,12 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     const uint32_t en = sm + M::C_EPBUF + (epar ^ 1) * (TU * EROW * 4);
                     cp_async4(en + (g * EROW + 4 * w + t4) * 4, ep + (size_t)yc0 * 128 + (4 * w + t4) * 4);
                     cp_async4(en + ((g + 8) * EROW + 4 * w + t4) * 4, ep + (size_t)yc1 * 128 + (4 * w + t4) * 4);
-                    cp_async_commit();
+                    // (no commit here: these two ride in the cp.async group of this sample's first layer step)
                 }
                 bar_compute();
 #pragma unroll
                 for (int j = 0; j < 4; j++) load_a(xa[j], sm + M::C_XBUF + j * 512 + lane16);
+                TRACE2(0, 2);
 
                 for (int l = 0; l < L; l++, pc++) {
                     const uint32_t sl = pc & 1, p1 = sm + M::C_RING + sl * M::PIECE0, fph = (pc >> 1) & 1;
@@ -1116,11 +1102,13 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                         st_async_v2(r_hbuf + (hcnt & 1) * 2048, h01, h23, r_hfull + 8 * (hcnt & 1));
                         hcnt++;
                     }
+                    TRACE2(0, 12);
                     prep(p1, false, ok_pf);
                     bar_compute();
                     uint32_t ha[4][4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) load_a(ha[j], sm + M::C_HBUF + j * 512 + lane16);
+                    TRACE2(0, 10);
                     float ra[4] = {0.f, 0.f, 0.f, 0.f}, rb[4] = {0.f, 0.f, 0.f, 0.f};
                     {
                         const uint4 bw0 = lds128(p1 + o_res), bw1 = lds128(p1 + o_res + 512);
@@ -1135,11 +1123,12 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                         sts64(sm + M::C_XBUF + xchg, x01, x23);
                         stg_v2(gring + lane16 + (size_t)((uint32_t)(it0.slot * L + l + 1) * rstride) + jw * 512 + hw * 8, x01, x23);
                     }
+                    TRACE2(0, 14);
                     if (DUMP) {
                         if (v0) { p.xtOut[((size_t)l * B + b0) * R + cw] = xres[0]; p.xtOut[((size_t)l * B + b0) * R + cw + 1] = xres[1]; }
                         if (v1) { p.xtOut[((size_t)l * B + b1) * R + cw] = xres[2]; p.xtOut[((size_t)l * B + b1) * R + cw + 1] = xres[3]; }
                     }
-                    stage_history();
+                    stage_step();                              // conditioning + history of three steps ahead
                     {   // look at the coming step's barriers
                         const uint32_t npc = pc + 1;
                         ok_f = mbar_try_a(s_full + 8 * (npc & 1), (npc >> 1) & 1);
@@ -1151,9 +1140,9 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
 #pragma unroll
                         for (int j = 0; j < 4; j++) load_a(xa[j], sm + M::C_XBUF + j * 512 + lane16);
                     }
-                    kp ^= 1;
+                    TRACE2(0, 11);
                 }
-                cp_async_wait_all();
+                cp_async_wait_pending<3>();                    // the previous-index rows rode in this sample's first group: long landed
                 epar ^= 1;
                 if (++it0.slot == slots) it0.slot = 0;
                 it0.t++;
@@ -1191,6 +1180,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                 for (int l = 0; l < L; l++, pc++, hcnt++) {
                     const uint32_t hb = sm + M::T_HBUF + (hcnt & 1) * 2048;
                     mbar_wait_a(s_hfull + 8 * (hcnt & 1), (hcnt >> 1) & 1);
+                    TRACE2(1, 16);
                     uint32_t ha[4][4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) load_a(ha[j], hb + j * 512 + lane16);
@@ -1211,6 +1201,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     if (tid == 0) mbar_expect_a(s_hfull + 8 * (hcnt & 1), 2048);
                     release_remote(s_hfree + 8 * (hcnt & 1));
                     release(s_empty + 8 * sl);
+                    TRACE2(1, 15);
                     if (DUMP) {
                         const float* pre = gbias + im.b_skpre + (size_t)l * S;
 #pragma unroll
@@ -1233,6 +1224,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
                 }
                 bar_compute();
+                TRACE2(1, 20);
                 float zz[4][4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -1271,6 +1263,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     zz[i][0] = zz[i][2] = s_bout[S + A + c]; zz[i][1] = zz[i][3] = s_bout[S + A + c + 1];
                 }
                 bar_compute();
+                TRACE2(1, 21);
 #pragma unroll
                 for (int q = 0; q < C::NQ_ZA; q++) out_gemm(C::OJP_ZA, sm + M::T_OB1, q * C::OJP_ZA);
 #pragma unroll
@@ -1284,6 +1277,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     }
                 }
                 bar_compute();
+                TRACE2(1, 22);
                 {   // softmax + categorical sample: warp w serves utterances 2w and 2w+1; lane holds 8 consecutive classes of each
                     float e[2][8], m[2] = {0.f, 0.f};
 #pragma unroll
@@ -1351,11 +1345,13 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                         }
                     }
                 }
+                TRACE2(1, 23);
                 bar_compute();
             }
             if (tid < TU && tile * TU + tid < B) { p.yCur[tile * TU + tid] = ys[tid]; p.yPrev[tile * TU + tid] = ys[TU + tid]; }
         }
     }
+#undef TRACE2
     // nobody leaves while the peer may still write into this CTA's shared memory or arrive on its barriers
     cluster_sync_all();
 }
@@ -1430,11 +1426,11 @@ static cudaError_t lat_launch_S(const WnParams& p, const unsigned char* im8, int
 }
 
 // the two-CTA cluster variant: grid = 2 x tiles, cluster (2, 1, 1)
-template <int S, bool DUMP>
+template <int S, bool DUMP, bool TRC>
 static cudaError_t lat2_go(const WnParams& pp, const unsigned char* im8, int tiles, int ntiles_alloc, cudaStream_t stream)
 {
     const size_t smem = CfgC<S>::SMEM;
-    cudaError_t e = cudaFuncSetAttribute(wn_lat2_kernel<S, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wn_lat2_kernel<S, DUMP, TRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * tiles, 1, 1);
@@ -1446,7 +1442,7 @@ static cudaError_t lat2_go(const WnParams& pp, const unsigned char* im8, int til
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, wn_lat2_kernel<S, DUMP>, pp, im8, ntiles_alloc);
+    e = cudaLaunchKernelEx(&cfg, wn_lat2_kernel<S, DUMP, TRC>, pp, im8, ntiles_alloc);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 template <int S>
@@ -1456,8 +1452,8 @@ static cudaError_t lat2_launch_S(const WnParams& p, const unsigned char* im8, in
     WnParams head = p, tail = p;
     if (p.dump) { head.count = p.count - 1; head.dump = 0; tail.init_sample = p.init_sample + p.count - 1; tail.count = 1; }
     cudaError_t e = cudaSuccess;
-    if (head.count > 0) e = lat2_go<S, false>(head, im8, tiles, ntiles_alloc, stream);
-    if (e == cudaSuccess && p.dump) e = lat2_go<S, true>(tail, im8, tiles, ntiles_alloc, stream);
+    if (head.count > 0) e = p.trace ? lat2_go<S, false, true>(head, im8, tiles, ntiles_alloc, stream) : lat2_go<S, false, false>(head, im8, tiles, ntiles_alloc, stream);
+    if (e == cudaSuccess && p.dump) e = lat2_go<S, true, false>(tail, im8, tiles, ntiles_alloc, stream);
     return e;
 }
 
@@ -1468,7 +1464,7 @@ cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, bo
     const unsigned char* im8 = static_cast<const unsigned char*>(image);
     size_t smem = 0;
     cudaError_t e;
-    if (cluster && !p.trace) {
+    if (cluster) {
         if (p.S == 256) e = lat2_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);
         else if (p.S == 128) e = lat2_launch_S<128>(p, im8, grid, ntiles_alloc, stream, &smem);
         else return cudaErrorInvalidValue;

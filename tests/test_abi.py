@@ -76,3 +76,22 @@ int main() {
         res = subprocess.run(cmd, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
         assert subprocess.run([exe]).returncode == 0
+
+
+def test_libc_selectors_replay_the_reference_draw():
+    """nvwn_libc_selectors (host helper, no GPU): Matrix(batch, samples).randomize(0.5, 1.0) on the caller's rand() stream
+    (pytorch/wavenet_infer.cu:92-93, matrix.cpp:38-56), checked against the glibc replay of tests/refgen.py."""
+    import ctypes as C
+
+    import numpy as np
+
+    from nv_wavenet_b200 import _lib
+    from tests import refgen
+    lib = _lib.lib()
+    B, N = 5, 7
+    C.CDLL(None).srand(321)
+    sel = np.empty(N * B, np.float32)
+    assert lib.nvwn_libc_selectors(C.c_void_p(sel.ctypes.data), B, N) == 0
+    want = refgen.randomize(refgen.GlibcRand(321), B, N, np.float32(0.5), np.float32(1.0)).reshape(N, B)
+    assert np.array_equal(sel.reshape(N, B), want)
+    assert lib.nvwn_libc_selectors(None, B, N) != 0

@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, ".")
 import os
 os.environ.setdefault("NVWN_FP16_KERNEL", "lat")
-os.environ.setdefault("NVWN_LAT_CLUSTER", "0")          # the timeline instrumentation lives in the single-CTA kernel
+# NVWN_LAT_CLUSTER=0 traces the single-CTA kernel; default: the cluster kernel (role 0 = chain CTA, role 1 = tail CTA)
 import nv_wavenet_b200 as nw
 from nv_wavenet_b200 import _lib
 from tests import refgen
@@ -28,7 +28,7 @@ e.run(N, B, None); torch.cuda.synchronize()
 buf = np.zeros(3 * 1024, np.uint64)
 assert lib.nvwn_debug_trace(e._h, T, buf.ctypes.data, 1) == 0
 names = {1: "sample start (ys read)", 2: "x0 built", 10: "h exchanged", 11: "layer done (x exchanged)", 12: "cur+prev GEMM issued", 13: "gate done",
-         14: "res done", 15: "skip issued", 16: "bg: h seen", 17: "bg: step start", 20: "relu(skip) exchanged", 21: "relu(Zs) exchanged", 22: "logits exchanged", 23: "sample done"}
+         14: "res done", 15: "skip issued", 16: "tail: h seen", 17: "bg: step start", 20: "relu(skip) exchanged", 21: "relu(Zs) exchanged", 22: "logits exchanged", 23: "sample done"}
 ev = []
 for role in range(3):
     for v in buf[role * 1024:(role + 1) * 1024]:
