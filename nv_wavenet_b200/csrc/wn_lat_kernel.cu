@@ -812,27 +812,29 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
 // The single-CTA kernel above runs at ~83 % of its SM's shared-memory bandwidth (per layer step: 72 KB written by TMA, 72 KB of
 // B fragments and 48 KB of A fragments read back; ncu: 0.57 LSU wavefronts per cycle + the TMA writes).  Here one 16-utterance tile
 // is served by a CLUSTER OF TWO CTAs on two SMs, which halves that traffic per SM:
-//   rank 0 "chain": embedding, cur / prev / res GEMMs, gate, history ring          ring pieces [Wcur_l | Wprev_l+1 | Wres_l] (40 KB)
-//   rank 1 "tail":  skip GEMM (one step behind, off the chain), Zs, Za, softmax, sampling      ring pieces Wskip_l and the output pieces
-// h goes chain -> tail through distributed shared memory (st.shared::cluster into a double-buffered tile + a remote mbarrier
-// arrive; the tail returns the buffer the same way); the sampled indices come back the same way once per sample.
+//   rank 0 "chain": embedding, cur / res GEMMs, gate, history ring writes             ring pieces [Wcur_l | Wres_l] (24 KB)
+//   rank 1 "tail":  everything that is not on the chain: the dilated-history GEMM Wprev . x[t-d] of the NEXT step, the skip GEMM of
+//                   this step, Zs, Za, softmax, sampling                              ring pieces Wprev_l+1, Wskip_l and the output pieces
+// Distributed shared memory carries three flows, all as st.async with complete_tx on a transaction barrier that the receiver arms
+// one phase ahead (data and signal travel together, no release fence on the sender), buffers handed back with relaxed remote arrives:
+// h (2 KB per step, chain -> tail), the history half of the next pre-activation (8 KB per step, tail -> chain), the 16 sampled
+// indices (once per sample, tail -> chain).
 constexpr int NTC = NCT + 32;
 
 template <int S>
 struct CfgC {
     using C = Cfg<S>;
-    static constexpr uint32_t PIECE0 = 40960;                              // chain: [Wcur | Wprev | Wres]
+    static constexpr uint32_t PIECE0 = 24576;                              // chain: [Wcur | Wres]
     static constexpr uint32_t SLOT1 = 32768;                               // tail: Wskip_l (S x 128 B) or an output piece
     static constexpr int NSLOT1 = 4;
     // chain CTA
     static constexpr uint32_t C_RING = 0;                                  // 2 x PIECE0
     static constexpr uint32_t C_EMB = 2 * PIECE0;
     static constexpr uint32_t C_EPBUF = C_EMB + A * EROW * 4;
-    static constexpr uint32_t C_PST = C_EPBUF + 2 * TU * EROW * 4;
-    static constexpr uint32_t C_XBUF = C_PST + 3 * 2048;
+    static constexpr uint32_t C_XBUF = C_EPBUF + 2 * TU * EROW * 4;
     static constexpr uint32_t C_HBUF = C_XBUF + 2048;
-    static constexpr uint32_t C_DIL = C_HBUF + 2048;
-    static constexpr uint32_t C_COND = C_DIL + MAXL * 4;                  // 4 x 4 KB: conditioning tiles, staged three steps ahead (cp.async)
+    static constexpr uint32_t C_AP = C_HBUF + 2048;                        // 2 x 8 KB: Wprev . x[t-d] of the coming step, written by the tail CTA
+    static constexpr uint32_t C_COND = C_AP + 2 * 8192;                    // 4 x 4 KB: conditioning tiles, staged three steps ahead (cp.async)
     static constexpr uint32_t C_BIAS = C_COND + 4 * 4096;                  // [L][8 warps][4][8] fp32: Bh / Bres pairs per thread
     static constexpr uint32_t C_END = C_BIAS + MAXL * 1024;
     // tail CTA
@@ -842,7 +844,9 @@ struct CfgC {
     static constexpr uint32_t T_OB0 = T_HBUF + 2 * 2048;
     static constexpr uint32_t T_OB1 = T_OB0 + (S / 16) * 512;
     static constexpr uint32_t T_LBUF = T_OB1 + (A / 16) * 512;
-    static constexpr uint32_t T_END = T_LBUF + TU * LROW * 4;
+    static constexpr uint32_t T_PST = T_LBUF + TU * LROW * 4;              // 4 x 2 KB: staged history tiles x[t-d] (A-fragment order)
+    static constexpr uint32_t T_DIL = T_PST + 4 * 2048;
+    static constexpr uint32_t T_END = T_DIL + MAXL * 4;
     // common tail of both maps (same offsets in both CTAs, so that remote addresses are computed with mapa on local ones)
     static constexpr uint32_t O_YS = (C_END > T_END ? C_END : T_END);
     static constexpr uint32_t O_BAR = O_YS + 2 * TU * 4;
@@ -859,6 +863,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)
 __device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t a, uint32_t b, uint32_t rbar)
 {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1,%2}, [%3];" ::"r"(raddr), "r"(a), "r"(b), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+                 ::"r"(raddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(rbar) : "memory");
 }
 __device__ __forceinline__ void st_async_u32(uint32_t raddr, uint32_t a, uint32_t rbar)
 {
@@ -895,20 +904,22 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
     const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
     constexpr int NQ = C::NQ_ZS + C::NQ_ZA;
 
-    // barriers (same offsets in both CTAs): ring full[4] / empty[4] (the chain uses two of each), pfull[3] (chain), hfull[2] (in the
-    // tail CTA, arrived by the chain's warps), hfree[2] and yfull (in the chain CTA, arrived by the tail's warps)
-    const uint32_t s_full = sm + M::O_BAR, s_empty = s_full + 32, s_pfull = s_full + 64, s_hfull = s_full + 88, s_hfree = s_full + 104, s_yfull = s_full + 120;
+    // barriers (same offsets in both CTAs): ring full[4] / empty[4] (the chain uses two of each); in the tail CTA: pfull[3] (staged
+    // history tiles), hfull[2] (h tiles, bytes from the chain), apfree[2]; in the chain CTA: hfree[2], yfull and apfull[2] (bytes from the tail)
+    const uint32_t s_full = sm + M::O_BAR, s_empty = s_full + 32, s_pfull = s_full + 64, s_hfull = s_full + 96, s_hfree = s_full + 112, s_yfull = s_full + 128;
+    const uint32_t s_apfull = s_full + 136, s_apfree = s_full + 152;
     int* ys = reinterpret_cast<int*>(smem_raw + M::O_YS);
     const uint32_t peer = crank ^ 1;
 
     if (tid == 0) {
         for (int i = 0; i < 4; i++) { mbar_init_a(s_full + 8 * i, 1); mbar_init_a(s_empty + 8 * i, NCW); }
-        for (int i = 0; i < 3; i++) mbar_init_a(s_pfull + 8 * i, 128);
-        for (int i = 0; i < 2; i++) { mbar_init_a(s_hfull + 8 * i, 1); mbar_init_a(s_hfree + 8 * i, NCW); }
+        for (int i = 0; i < 4; i++) mbar_init_a(s_pfull + 8 * i, 128);
+        for (int i = 0; i < 2; i++) { mbar_init_a(s_hfull + 8 * i, 1); mbar_init_a(s_hfree + 8 * i, NCW); mbar_init_a(s_apfull + 8 * i, 1); mbar_init_a(s_apfree + 8 * i, NCW); }
         mbar_init_a(s_yfull, 1);
         fence_mbar_init();
         // transaction barriers are armed by their owner one phase ahead: the tail expects 2 KB per h tile, the chain 128 B of indices
-        if (is_chain) mbar_expect_a(s_yfull, 2 * TU * 4);
+        // and 8 KB per pre-activation tile
+        if (is_chain) { mbar_expect_a(s_yfull, 2 * TU * 4); mbar_expect_a(s_apfull, 8192); mbar_expect_a(s_apfull + 8, 8192); }
         else { mbar_expect_a(s_hfull, 2048); mbar_expect_a(s_hfull + 8, 2048); }
     }
     if (tid < TU) {
@@ -917,12 +928,12 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
         ys[TU + tid] = b < B ? p.yPrev[b] : 128;
     }
     if (is_chain) {
-        int* dil = reinterpret_cast<int*>(smem_raw + M::C_DIL);
-        if (tid == 0) { int d = 1; for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; } }
         const uint32_t* ec = static_cast<const uint32_t*>(p.embCur);
         for (int i = tid; i < A * 32; i += NTC) sts32(sm + M::C_EMB + ((i >> 5) * EROW + (i & 31)) * 4, ec[i]);
         for (int i = tid; i < L * 256; i += NTC) sts32(sm + M::C_BIAS + i * 4, __float_as_uint(gbias[im.b_layer + i]));
     } else {
+        int* dil = reinterpret_cast<int*>(smem_raw + M::T_DIL);
+        if (tid == 0) { int d = 1; for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; } }   // nv_wavenet.cuh:99-111
         float* s_bout = reinterpret_cast<float*>(smem_raw + M::T_BOUT);
         for (int i = tid; i < S; i += NTC) s_bout[i] = gbias[im.b_skpre + (size_t)(L - 1) * S + i];
         for (int i = tid; i < A; i += NTC) { s_bout[S + i] = gbias[im.b_bzs + i]; s_bout[S + A + i] = gbias[im.b_bza + i]; }
@@ -949,91 +960,62 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                         const uint32_t sl = pc & 1;
                         mbar_wait_a(s_empty + 8 * sl, ((pc >> 1) & 1) ^ 1);
                         mbar_expect_a(s_full + 8 * sl, M::PIECE0);
-                        tma_load_a(sm + M::C_RING + sl * M::PIECE0, img + (size_t)l * im.layer_bytes, M::PIECE0, s_full + 8 * sl);
+                        tma_load_a(sm + M::C_RING + sl * M::PIECE0, img + (size_t)l * im.layer_bytes + C::W_CUR, 16384, s_full + 8 * sl);
+                        tma_load_a(sm + M::C_RING + sl * M::PIECE0 + 16384, img + (size_t)l * im.layer_bytes + C::W_RES, 8192, s_full + 8 * sl);
                     }
             }
         } else {
-            int* dil = reinterpret_cast<int*>(smem_raw + M::C_DIL);
             const uint32_t cstride = (uint32_t)ntiles_alloc * 4096u, rstride = (uint32_t)ntiles_alloc * 2048u;
             const unsigned char* gcond = static_cast<const unsigned char*>(p.Lh) + (size_t)tile * 4096 + (size_t)(w * 32 + lane) * 16;
             unsigned char* gring = static_cast<unsigned char*>(p.ring) + (size_t)tile * 2048;
             const int cw = 8 * w + 2 * t4;
-            const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16, o_res = 32768u + (uint32_t)(w * 2) * 512 + lane16;
+            const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16, o_res = 16384u + (uint32_t)(w * 2) * 512 + lane16;
             const uint32_t r_hbuf = mapa_u32(sm + M::T_HBUF + xchg, 1);            // this thread's slot of the tail CTA's h tiles
             const uint32_t r_hfull = mapa_u32(s_hfull, 1);
             const uint32_t s_bias = sm + M::C_BIAS + (uint32_t)(w * 4 + t4) * 32;   // this thread's Bh / Bres pairs of layer 0 (+ 1 KB per layer)
             const uint32_t s_cond = sm + M::C_COND + (uint32_t)(w * 32 + lane) * 16;  // this thread's 16 B of a conditioning tile (+ 4 KB per slot)
-            auto advance = [&](StepIt& it) { if (++it.l == L) { it.l = 0; it.t++; if (++it.slot == slots) it.slot = 0; } };
-            // Staging of the step `itp` (three steps ahead of its use), no register and no scoreboard involved:
-            //  * its conditioning tile: every thread copies the 16 bytes it will read back itself (cp.async; completion = the thread's
-            //    own cp.async group, no barrier) into a 4-slot ring;
-            //  * its dilated history x_l[t-d] (zero before the start of the utterance, nv_wavenet.cuh:106): warps 0-3, 128 x 16 B, into
-            //    a 3-slot ring, completion on an mbarrier (every warp reads the whole tile).
-            StepIt itp{t_begin, 0, t_begin % slots};
+            const uint32_t s_ap = sm + M::C_AP + (uint32_t)(w * 32 + lane) * 32;    // this thread's 8 floats of a pre-activation tile (+ 8 KB per buffer)
+            // Conditioning of the step `itp` (three steps ahead of its use), no register and no scoreboard involved: every thread copies
+            // the 16 bytes it will read back itself (cp.async; completion = the thread's own cp.async group, no barrier) into a 4-slot ring.
+            int tp = t_begin, lp = 0;
             uint32_t pcnt = 0;
             const unsigned char* cptr = gcond + (size_t)t_begin * L * cstride;         // conditioning of step itp (steps are consecutive in memory)
             auto stage_step = [&]() {
-                if (itp.t < t_end) cp_async16(s_cond + (pcnt & 3) * 4096, cptr);
+                if (tp < t_end) cp_async16(s_cond + (pcnt & 3) * 4096, cptr);
                 cptr += cstride;
-                if (w < 4) {
-                    const uint32_t slot3 = pcnt % 3;
-                    const int d = dil[itp.l];
-                    const uint32_t dst = sm + M::C_PST + slot3 * 2048 + (uint32_t)(w * 32 + lane) * 16;
-                    if (itp.t >= t_end || itp.t < d) {
-                        sts128(dst, make_uint4(0, 0, 0, 0));
-                        mbar_arrive_a(s_pfull + 8 * slot3);
-                    } else {
-                        int sl = itp.slot - d; if (sl < 0) sl += slots;
-                        cp_async16(dst, gring + (size_t)((uint32_t)(sl * L + itp.l) * rstride) + (size_t)(w * 32 + lane) * 16);
-                        cp_async_arrive_noinc(s_pfull + 8 * slot3);
-                    }
-                }
                 cp_async_commit();
                 pcnt++;
-                advance(itp);
+                if (++lp == L) { lp = 0; tp++; }
             };
             uint32_t xa[4][4];
             float accp[2][4];
             float2 brn = make_float2(0.f, 0.f);
             float xres[4] = {0.f, 0.f, 0.f, 0.f};
-            StepIt it1{0, 0, 0};
+            int t1 = t_begin, l1 = 0;                          // the coming step (number pn)
             uint32_t pn = 0;
-            // accp <- (Bh + Lh) + Wprev . x[t-d] of the coming step it1 (staged tile number pn); everything it reads is in shared memory
-            auto prep = [&](const uint32_t p1, const bool from_global, const bool pf_ok) {
-                const uint32_t slot3 = pn % 3;
-                if (it1.t < t_end) {
-                    uint4 bt0, bg0, bt1, bg1;
-                    if (from_global) {
-                        const unsigned char* gp = img + (size_t)(L - 1) * im.layer_bytes + C::W_PREV;
-                        bt0 = ldg_nc_v4(gp + o_t0); bg0 = ldg_nc_v4(gp + o_g0); bt1 = ldg_nc_v4(gp + o_t0 + 512); bg1 = ldg_nc_v4(gp + o_g0 + 512);
-                        cp_async_wait_all();
-                    } else {
-                        bt0 = lds128(p1 + C::W_PREV + o_t0); bg0 = lds128(p1 + C::W_PREV + o_g0);
-                        bt1 = lds128(p1 + C::W_PREV + o_t0 + 512); bg1 = lds128(p1 + C::W_PREV + o_g0 + 512);
-                        cp_async_wait_pending<1>();            // this thread's conditioning of step it1 has landed (the group of the step after may be in flight)
-                    }
+            // accp <- (Bh + Lh) + [Wprev . x[t-d], from the tail CTA] of the coming step; everything it reads is in shared memory
+            auto prep = [&](const bool ap_ok) {
+                if (t1 < t_end) {
+                    cp_async_wait_pending<1>();                // this thread's conditioning of that step has landed (the group of the step after may be in flight)
                     const uint4 cb = lds128(s_cond + (pn & 3) * 4096);
-                    const uint4 bq = lds128(s_bias + it1.l * 1024);
-                    const uint4 b2 = lds128(s_bias + it1.l * 1024 + 16);
+                    const uint4 bq = lds128(s_bias + l1 * 1024);
+                    const uint4 b2 = lds128(s_bias + l1 * 1024 + 16);
+                    if (!ap_ok) mbar_wait_a(s_apfull + 8 * (pn & 1), (pn >> 1) & 1);
+                    const uint4 a0 = lds128(s_ap + (pn & 1) * 8192), a1 = lds128(s_ap + (pn & 1) * 8192 + 16);
                     const float4 bh = make_float4(__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z), __uint_as_float(bq.w));
                     brn = make_float2(__uint_as_float(b2.x), __uint_as_float(b2.y));
-                    {
-                        const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
-                        accp[0][0] = bh.x + c0.x; accp[0][1] = bh.y + c0.y; accp[0][2] = bh.x + c1.x; accp[0][3] = bh.y + c1.y;
-                        accp[1][0] = bh.z + c2.x; accp[1][1] = bh.w + c2.y; accp[1][2] = bh.z + c3.x; accp[1][3] = bh.w + c3.y;
-                    }
-                    if (!pf_ok) mbar_wait_a(s_pfull + 8 * slot3, (pn / 3) & 1);
-                    uint32_t pb[4][4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) load_a(pb[j], sm + M::C_PST + slot3 * 2048 + j * 512 + lane16);
-                    float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
-                    hmma(accp[0], pb[0], bt0.x, bt0.y); hmma(accp[1], pb[0], bg0.x, bg0.y); hmma(u0, pb[2], bt1.x, bt1.y); hmma(u1, pb[2], bg1.x, bg1.y);
-                    hmma(accp[0], pb[1], bt0.z, bt0.w); hmma(accp[1], pb[1], bg0.z, bg0.w); hmma(u0, pb[3], bt1.z, bt1.w); hmma(u1, pb[3], bg1.z, bg1.w);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { accp[0][i] += u0[i]; accp[1][i] += u1[i]; }
+                    const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
+                    accp[0][0] = (bh.x + c0.x) + __uint_as_float(a0.x); accp[0][1] = (bh.y + c0.y) + __uint_as_float(a0.y);
+                    accp[0][2] = (bh.x + c1.x) + __uint_as_float(a0.z); accp[0][3] = (bh.y + c1.y) + __uint_as_float(a0.w);
+                    accp[1][0] = (bh.z + c2.x) + __uint_as_float(a1.x); accp[1][1] = (bh.w + c2.y) + __uint_as_float(a1.y);
+                    accp[1][2] = (bh.z + c3.x) + __uint_as_float(a1.z); accp[1][3] = (bh.w + c3.y) + __uint_as_float(a1.w);
+                    // the tile has been read: arm its barrier for the tile after next (one thread, ordered before this warp's "free"
+                    // signal), then hand the buffer back to the tail CTA
+                    if (tid == 0) mbar_expect_a(s_apfull + 8 * (pn & 1), 8192);
+                    release_remote(s_apfree + 8 * (pn & 1));
                 }
                 pn++;
-                advance(it1);
+                if (++l1 == L) { l1 = 0; t1++; }
             };
             {   // prologue: previous-index rows of the first sample; staging of steps 0, 1, 2; pre-activation of step 0
                 const uint32_t* ep = static_cast<const uint32_t*>(p.embPrev);
@@ -1042,12 +1024,11 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
             }
             StepIt it0{t_begin, 0, t_begin % slots};
             stage_step(); stage_step(); stage_step();
-            it1 = it0;
-            prep(0, true, false);                                       // leaves it1 = step 1
+            prep(false);                                       // step 0 (its history half was shipped by the tail's prologue)
             bar_compute();
 
             uint32_t pc = 0, epar = 0, hcnt = 0;               // ring piece counter, sample parity, h tiles handed over
-            bool ok_f = false, ok_pf = false, ok_hf = false;
+            bool ok_f = false, ok_ap = false, ok_hf = false;
             for (int t = t_begin; t < t_end; t++) {
                 TRACE2(0, 1);
                 if (t > t_begin) {                             // the tail CTA has written this sample's indices into ys
@@ -1103,7 +1084,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                         hcnt++;
                     }
                     TRACE2(0, 12);
-                    prep(p1, false, ok_pf);
+                    prep(ok_ap);
                     bar_compute();
                     uint32_t ha[4][4];
 #pragma unroll
@@ -1128,11 +1109,11 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                         if (v0) { p.xtOut[((size_t)l * B + b0) * R + cw] = xres[0]; p.xtOut[((size_t)l * B + b0) * R + cw + 1] = xres[1]; }
                         if (v1) { p.xtOut[((size_t)l * B + b1) * R + cw] = xres[2]; p.xtOut[((size_t)l * B + b1) * R + cw + 1] = xres[3]; }
                     }
-                    stage_step();                              // conditioning + history of three steps ahead
+                    stage_step();                              // conditioning of three steps ahead
                     {   // look at the coming step's barriers
                         const uint32_t npc = pc + 1;
                         ok_f = mbar_try_a(s_full + 8 * (npc & 1), (npc >> 1) & 1);
-                        ok_pf = mbar_try_a(s_pfull + 8 * (pn % 3), (pn / 3) & 1);
+                        ok_ap = mbar_try_a(s_apfull + 8 * (pn & 1), (pn >> 1) & 1);
                         ok_hf = mbar_try_a(s_hfree + 8 * (hcnt & 1), ((hcnt >> 1) & 1) ^ 1);
                     }
                     if (l + 1 < L) {
@@ -1161,7 +1142,11 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     pc++;
                 };
                 for (int t = t_begin; t < t_end; t++) {
-                    for (int l = 0; l < L; l++) put(img + (size_t)l * im.layer_bytes + C::W_SKIP, S * 128);
+                    for (int l = 0; l < L; l++) {
+                        // Wprev of the layer two steps ahead lives in the block of the layer before it (lat_pack_kernel), then this step's Wskip
+                        put(img + (size_t)((l + 1) % L) * im.layer_bytes + C::W_PREV, 16384);
+                        put(img + (size_t)l * im.layer_bytes + C::W_SKIP, S * 128);
+                    }
                     for (int q = 0; q < NQ; q++)
                         put(q < C::NQ_ZS ? img + im.off_zs + (size_t)q * C::ZS_PIECE : img + im.off_za + (size_t)(q - C::NQ_ZS) * C::ZA_PIECE,
                             q < C::NQ_ZS ? C::ZS_PIECE : C::ZA_PIECE);
@@ -1173,11 +1158,74 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
             float sk[C::NSK][4];
 #pragma unroll
             for (int i = 0; i < C::NSK; i++) sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
+            // ---- the dilated-history half of the pre-activations, two steps ahead of the chain CTA
+            int* dil = reinterpret_cast<int*>(smem_raw + M::T_DIL);
+            const uint32_t rstride = (uint32_t)ntiles_alloc * 2048u;
+            const unsigned char* gring = static_cast<const unsigned char*>(p.ring) + (size_t)tile * 2048;
+            const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16;
+            const uint32_t r_ap = mapa_u32(sm + M::C_AP + (uint32_t)(w * 32 + lane) * 32, 0);   // this thread's 8 floats of the chain CTA's tiles
+            const uint32_t r_apfull = mapa_u32(s_apfull, 0);
+            auto advance = [&](StepIt& it) { if (++it.l == L) { it.l = 0; it.t++; if (++it.slot == slots) it.slot = 0; } };
+            // history tile x_l[t-d] of the step `itp` (zero before the start of the utterance, nv_wavenet.cuh:106): warps 0-3, 128 x 16 B,
+            // into a 4-slot ring, completion on an mbarrier (every warp reads the whole tile); staged two steps before its use
+            StepIt itp{t_begin, 0, t_begin % slots};
+            uint32_t pcnt = 0;
+            auto stage_history = [&]() {
+                if (w < 4) {
+                    const uint32_t slot4 = pcnt & 3;
+                    const int d = dil[itp.l];
+                    const uint32_t dst = sm + M::T_PST + slot4 * 2048 + (uint32_t)(w * 32 + lane) * 16;
+                    if (itp.t >= t_end || itp.t < d) {
+                        sts128(dst, make_uint4(0, 0, 0, 0));
+                        mbar_arrive_a(s_pfull + 8 * slot4);
+                    } else {
+                        int sl = itp.slot - d; if (sl < 0) sl += slots;
+                        cp_async16(dst, gring + (size_t)((uint32_t)(sl * L + itp.l) * rstride) + (size_t)(w * 32 + lane) * 16);
+                        cp_async_arrive_noinc(s_pfull + 8 * slot4);
+                    }
+                }
+                pcnt++;
+                advance(itp);
+            };
+            int t1 = t_begin, l1 = 0;                          // the step whose history half is computed next (number pn)
+            uint32_t pn = 0;
+            // Wprev . x[t-d] of step pn -> the chain CTA's pre-activation tile pn & 1 (free once the chain has read tile pn - 2)
+            auto prev_gemm = [&](const uint4 bt0, const uint4 bg0, const uint4 bt1, const uint4 bg1) {
+                if (t1 < t_end) {
+                    const uint32_t slot4 = pn & 3;
+                    mbar_wait_a(s_pfull + 8 * slot4, (pn >> 2) & 1);
+                    uint32_t pb[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) load_a(pb[j], sm + M::T_PST + slot4 * 2048 + j * 512 + lane16);
+                    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
+                    hmma(a0, pb[0], bt0.x, bt0.y); hmma(a1, pb[0], bg0.x, bg0.y); hmma(u0, pb[2], bt1.x, bt1.y); hmma(u1, pb[2], bg1.x, bg1.y);
+                    hmma(a0, pb[1], bt0.z, bt0.w); hmma(a1, pb[1], bg0.z, bg0.w); hmma(u0, pb[3], bt1.z, bt1.w); hmma(u1, pb[3], bg1.z, bg1.w);
+                    mbar_wait_a(s_apfree + 8 * (pn & 1), ((pn >> 1) & 1) ^ 1);
+                    st_async_v4(r_ap + (pn & 1) * 8192, a0[0] + u0[0], a0[1] + u0[1], a0[2] + u0[2], a0[3] + u0[3], r_apfull + 8 * (pn & 1));
+                    st_async_v4(r_ap + (pn & 1) * 8192 + 16, a1[0] + u1[0], a1[1] + u1[1], a1[2] + u1[2], a1[3] + u1[3], r_apfull + 8 * (pn & 1));
+                }
+                pn++;
+                if (++l1 == L) { l1 = 0; t1++; }
+            };
+            stage_history(); stage_history(); stage_history(); stage_history();
+            for (int k = 0; k < 2; k++) {                      // prologue: steps 0 and 1, weights straight from the image
+                const unsigned char* gp = img + (size_t)((k + L - 1) % L) * im.layer_bytes + C::W_PREV;
+                prev_gemm(ldg_nc_v4(gp + o_t0), ldg_nc_v4(gp + o_g0), ldg_nc_v4(gp + o_t0 + 512), ldg_nc_v4(gp + o_g0 + 512));
+            }
             uint32_t pc = 0, hcnt = 0;
             for (int t = t_begin; t < t_end; t++) {
                 const float sel0 = (2 * w + 0 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w] : 0.5f;
                 const float sel1 = (2 * w + 1 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w + 1] : 0.5f;
                 for (int l = 0; l < L; l++, pc++, hcnt++) {
+                    {   // off the chain: the history half of the step after next, then the staging of the tile four steps ahead
+                        const uint32_t sa = pc & 3, pa = sm + M::T_RING + sa * M::SLOT1;
+                        mbar_wait_a(s_full + 8 * sa, (pc >> 2) & 1);
+                        const uint4 bt0 = lds128(pa + o_t0), bg0 = lds128(pa + o_g0), bt1 = lds128(pa + o_t0 + 512), bg1 = lds128(pa + o_g0 + 512);
+                        prev_gemm(bt0, bg0, bt1, bg1);
+                        release(s_empty + 8 * sa);
+                        pc++;
+                        stage_history();
+                    }
                     const uint32_t hb = sm + M::T_HBUF + (hcnt & 1) * 2048;
                     mbar_wait_a(s_hfull + 8 * (hcnt & 1), (hcnt >> 1) & 1);
                     TRACE2(1, 16);
@@ -1361,7 +1409,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
 // ------------------------------------------------------------------------------------------------ host side
 bool wn_lat_supported(int R_, int S, int A_, int L)
 {
-    return R_ == R && A_ == A && (S == 128 || S == 256) && L >= 4 && L <= MAXL;     // L >= 4: history prefetch runs 3 steps ahead
+    return R_ == R && A_ == A && (S == 128 || S == 256) && L >= 4 && L <= MAXL;     // L >= 4: history prefetch runs 3 steps ahead (single-CTA kernel)
 }
 int wn_lat_tiles(int B) { return (B + TU - 1) / TU; }
 size_t wn_lat_image_bytes(int S, int L) { return lat_image(S, L).total; }
@@ -1464,7 +1512,8 @@ cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, bo
     const unsigned char* im8 = static_cast<const unsigned char*>(image);
     size_t smem = 0;
     cudaError_t e;
-    if (cluster) {
+    // the cluster kernel's tail CTA reads history tiles the chain CTA wrote at least L - 5 steps earlier: it wants a few steps of margin
+    if (cluster && p.L >= 8) {
         if (p.S == 256) e = lat2_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);
         else if (p.S == 128) e = lat2_launch_S<128>(p, im8, grid, ntiles_alloc, stream, &smem);
         else return cudaErrorInvalidValue;
