@@ -96,7 +96,7 @@ struct nvwn_engine {
     bool tc_mode = false;                    // decided once at creation: conditioning + history use the tiled layouts
     int tc_tile = 64;                        // utterances per tensor-core tile and its schedule: resolved ONCE at creation (the
     bool tc_fused = false;                   // conditioning store, the history ring and every launch depend on them)
-    bool lat_cluster = true;                 // latency mode: a two-CTA cluster per tile while 2 x tiles fit one wave (NVWN_LAT_CLUSTER=0 disables; read once)
+    bool lat_cluster = true;                 // latency mode: a three-CTA cluster per tile while 3 x tiles fit one wave (NVWN_LAT_CLUSTER=0 disables; read once)
     bool lat_mode = false;                   // decided once at creation: latency-mode kernel (fragment-ordered layouts); tc_image holds its weight image
 
     float* lut_f = nullptr;                  // mu-law decode tables (nvwn_get_audio): A floats, then 2 x A int16 (wrap / saturate)
@@ -505,7 +505,7 @@ int nvwn_run_partial(nvwn_engine* e, int init_sample, int count, int num_samples
                 CK(wn_lat_pack(e->tc_image, p, stream));
                 e->tc_dirty = false;
             }
-            CK(wn_launch_lat(p, e->tc_image, e->B, e->lat_cluster && (batch_size + 15) / 16 <= 74, stream, &e->last));
+            CK(wn_launch_lat(p, e->tc_image, e->B, e->lat_cluster, stream, &e->last));
         } else if (e->tc_mode) {
             if (batch_size != e->B)
                 return fail(NVWN_EINVAL, "nvwn_run_partial: the tensor-core path needs batch_size equal to the engine's batch size");

@@ -113,6 +113,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
@@ -167,6 +173,13 @@ __device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// a look that never suspends the thread (try_wait parks it until a time limit when the phase is still running)
+__device__ __forceinline__ bool mbar_probe_a(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
 // three looks issued back to back: their ~90-cycle latencies overlap
@@ -813,12 +826,13 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
 // B fragments and 48 KB of A fragments read back; ncu: 0.57 LSU wavefronts per cycle + the TMA writes).  Here one 16-utterance tile
 // is served by a CLUSTER OF TWO CTAs on two SMs, which halves that traffic per SM:
 //   rank 0 "chain": embedding, cur / res GEMMs, gate, history ring writes             ring pieces [Wcur_l | Wres_l] (24 KB)
-//   rank 1 "tail":  everything that is not on the chain: the dilated-history GEMM Wprev . x[t-d] of the NEXT step, the skip GEMM of
-//                   this step, Zs, Za, softmax, sampling                              ring pieces Wprev_l+1, Wskip_l and the output pieces
+//   rank 1 "tail":  skip GEMM of every step (off the chain), Zs, Za, softmax, sampling ring pieces Wskip_l and the output pieces
+//   rank 2 "prep":  (Bh + Lh) + Wprev . x[t-d] of the steps to come, up to NAP ahead   ring pieces Wprev_l (16 KB)
 // Distributed shared memory carries three flows, all as st.async with complete_tx on a transaction barrier that the receiver arms
 // one phase ahead (data and signal travel together, no release fence on the sender), buffers handed back with relaxed remote arrives:
-// h (2 KB per step, chain -> tail), the history half of the next pre-activation (8 KB per step, tail -> chain), the 16 sampled
-// indices (once per sample, tail -> chain).
+// h (2 KB per step, chain -> tail), the pre-activation before the current-sample GEMM (8 KB per step, prep -> chain), the 16 sampled
+// indices (once per sample, tail -> chain).  Each CTA moves less than ~100 KB per step through its shared memory; a single CTA
+// doing all of it moves ~190 KB per step and is bound by that.
 constexpr int NTC = NCT + 32;
 
 template <int S>
@@ -827,15 +841,16 @@ struct CfgC {
     static constexpr uint32_t PIECE0 = 24576;                              // chain: [Wcur | Wres]
     static constexpr uint32_t SLOT1 = 32768;                               // tail: Wskip_l (S x 128 B) or an output piece
     static constexpr int NSLOT1 = 4;
+    static constexpr int NAP = 4;                                          // pre-activation tiles in flight from the prep CTA to the chain CTA
+    static constexpr int NPS = 8;                                          // staged history / conditioning tiles of the prep CTA
     // chain CTA
     static constexpr uint32_t C_RING = 0;                                  // 2 x PIECE0
     static constexpr uint32_t C_EMB = 2 * PIECE0;
     static constexpr uint32_t C_EPBUF = C_EMB + A * EROW * 4;
     static constexpr uint32_t C_XBUF = C_EPBUF + 2 * TU * EROW * 4;
     static constexpr uint32_t C_HBUF = C_XBUF + 2048;
-    static constexpr uint32_t C_AP = C_HBUF + 2048;                        // 2 x 8 KB: Wprev . x[t-d] of the coming step, written by the tail CTA
-    static constexpr uint32_t C_COND = C_AP + 2 * 8192;                    // 4 x 4 KB: conditioning tiles, staged three steps ahead (cp.async)
-    static constexpr uint32_t C_BIAS = C_COND + 4 * 4096;                  // [L][8 warps][4][8] fp32: Bh / Bres pairs per thread
+    static constexpr uint32_t C_AP = C_HBUF + 2048;                        // NAP x 8 KB: (Bh + Lh) + Wprev . x[t-d] of the coming steps, written by the prep CTA
+    static constexpr uint32_t C_BIAS = C_AP + NAP * 8192;                  // [L][8 warps][4][8] fp32: Bh / Bres pairs per thread (Bres is read here)
     static constexpr uint32_t C_END = C_BIAS + MAXL * 1024;
     // tail CTA
     static constexpr uint32_t T_RING = 0;                                  // NSLOT1 x SLOT1
@@ -844,14 +859,20 @@ struct CfgC {
     static constexpr uint32_t T_OB0 = T_HBUF + 2 * 2048;
     static constexpr uint32_t T_OB1 = T_OB0 + (S / 16) * 512;
     static constexpr uint32_t T_LBUF = T_OB1 + (A / 16) * 512;
-    static constexpr uint32_t T_PST = T_LBUF + TU * LROW * 4;              // 4 x 2 KB: staged history tiles x[t-d] (A-fragment order)
-    static constexpr uint32_t T_DIL = T_PST + 4 * 2048;
-    static constexpr uint32_t T_END = T_DIL + MAXL * 4;
-    // common tail of both maps (same offsets in both CTAs, so that remote addresses are computed with mapa on local ones)
-    static constexpr uint32_t O_YS = (C_END > T_END ? C_END : T_END);
+    static constexpr uint32_t T_END = T_LBUF + TU * LROW * 4;
+    // prep CTA
+    static constexpr uint32_t P_RING = 0;                                  // 4 x 16 KB: Wprev_l
+    static constexpr uint32_t P_PST = 4 * 16384;                           // NPS x 2 KB: staged history tiles x[t-d] (A-fragment order)
+    static constexpr uint32_t P_COND = P_PST + NPS * 2048;                 // NPS x 4 KB: conditioning tiles, staged with the history tiles (cp.async)
+    static constexpr uint32_t P_BIAS = P_COND + NPS * 4096;                // [L][8 warps][4][4] fp32: this thread's Bh
+    static constexpr uint32_t P_DIL = P_BIAS + MAXL * 512;
+    static constexpr uint32_t P_END = P_DIL + MAXL * 4;
+    // common tail of the maps (same offsets in every CTA, so that remote addresses are computed with mapa on local ones)
+    static constexpr uint32_t O_YS = (C_END > T_END ? (C_END > P_END ? C_END : P_END) : (T_END > P_END ? T_END : P_END));
     static constexpr uint32_t O_BAR = O_YS + 2 * TU * 4;
-    static constexpr uint32_t SMEM = O_BAR + 24 * 8;
+    static constexpr uint32_t SMEM = O_BAR + 32 * 8;
 };
+constexpr int NCL = 3;                       // CTAs per cluster
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)
 {
@@ -897,30 +918,31 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const bool is_chain = crank == 0;
-    const int tile = blockIdx.x >> 1;
+    const bool is_chain = crank == 0, is_tail = crank == 1;
+    const int tile = blockIdx.x / NCL;
     const int slots = p.maxDil + 1;
     const int t_begin = p.init_sample, t_end = p.init_sample + p.count;
     const float* gbias = reinterpret_cast<const float*>(img + im.off_bias);
     constexpr int NQ = C::NQ_ZS + C::NQ_ZA;
 
-    // barriers (same offsets in both CTAs): ring full[4] / empty[4] (the chain uses two of each); in the tail CTA: pfull[3] (staged
-    // history tiles), hfull[2] (h tiles, bytes from the chain), apfree[2]; in the chain CTA: hfree[2], yfull and apfull[2] (bytes from the tail)
-    const uint32_t s_full = sm + M::O_BAR, s_empty = s_full + 32, s_pfull = s_full + 64, s_hfull = s_full + 96, s_hfree = s_full + 112, s_yfull = s_full + 128;
-    const uint32_t s_apfull = s_full + 136, s_apfree = s_full + 152;
+    // barriers (same offsets in every CTA): ring full[4] / empty[4] (the chain uses two of each); pfull[NPS] (prep: staged history
+    // tiles); hfull[2] (tail: h tiles, bytes from the chain); hfree[2], yfull, apfull[NAP] (chain: bytes from the tail / the prep CTA);
+    // apfree[NAP] (prep: arrived by the chain's warps)
+    const uint32_t s_full = sm + M::O_BAR, s_empty = s_full + 32, s_pfull = s_full + 64, s_hfull = s_full + 128, s_hfree = s_full + 144, s_yfull = s_full + 160;
+    const uint32_t s_apfull = s_full + 168, s_apfree = s_full + 200;
     int* ys = reinterpret_cast<int*>(smem_raw + M::O_YS);
-    const uint32_t peer = crank ^ 1;
 
     if (tid == 0) {
         for (int i = 0; i < 4; i++) { mbar_init_a(s_full + 8 * i, 1); mbar_init_a(s_empty + 8 * i, NCW); }
-        for (int i = 0; i < 4; i++) mbar_init_a(s_pfull + 8 * i, 128);
-        for (int i = 0; i < 2; i++) { mbar_init_a(s_hfull + 8 * i, 1); mbar_init_a(s_hfree + 8 * i, NCW); mbar_init_a(s_apfull + 8 * i, 1); mbar_init_a(s_apfree + 8 * i, NCW); }
+        for (int i = 0; i < M::NPS; i++) mbar_init_a(s_pfull + 8 * i, 128);
+        for (int i = 0; i < 2; i++) { mbar_init_a(s_hfull + 8 * i, 1); mbar_init_a(s_hfree + 8 * i, NCW); }
+        for (int i = 0; i < M::NAP; i++) { mbar_init_a(s_apfull + 8 * i, 1); mbar_init_a(s_apfree + 8 * i, NCW); }
         mbar_init_a(s_yfull, 1);
         fence_mbar_init();
         // transaction barriers are armed by their owner one phase ahead: the tail expects 2 KB per h tile, the chain 128 B of indices
         // and 8 KB per pre-activation tile
-        if (is_chain) { mbar_expect_a(s_yfull, 2 * TU * 4); mbar_expect_a(s_apfull, 8192); mbar_expect_a(s_apfull + 8, 8192); }
-        else { mbar_expect_a(s_hfull, 2048); mbar_expect_a(s_hfull + 8, 2048); }
+        if (is_chain) { mbar_expect_a(s_yfull, 2 * TU * 4); for (int i = 0; i < M::NAP; i++) mbar_expect_a(s_apfull + 8 * i, 8192); }
+        else if (is_tail) { mbar_expect_a(s_hfull, 2048); mbar_expect_a(s_hfull + 8, 2048); }
     }
     if (tid < TU) {
         const int b = tile * TU + tid;
@@ -931,15 +953,17 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
         const uint32_t* ec = static_cast<const uint32_t*>(p.embCur);
         for (int i = tid; i < A * 32; i += NTC) sts32(sm + M::C_EMB + ((i >> 5) * EROW + (i & 31)) * 4, ec[i]);
         for (int i = tid; i < L * 256; i += NTC) sts32(sm + M::C_BIAS + i * 4, __float_as_uint(gbias[im.b_layer + i]));
-    } else {
-        int* dil = reinterpret_cast<int*>(smem_raw + M::T_DIL);
-        if (tid == 0) { int d = 1; for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; } }   // nv_wavenet.cuh:99-111
+    } else if (is_tail) {
         float* s_bout = reinterpret_cast<float*>(smem_raw + M::T_BOUT);
         for (int i = tid; i < S; i += NTC) s_bout[i] = gbias[im.b_skpre + (size_t)(L - 1) * S + i];
         for (int i = tid; i < A; i += NTC) { s_bout[S + i] = gbias[im.b_bzs + i]; s_bout[S + A + i] = gbias[im.b_bza + i]; }
+    } else {
+        int* dil = reinterpret_cast<int*>(smem_raw + M::P_DIL);
+        if (tid == 0) { int d = 1; for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; } }   // nv_wavenet.cuh:99-111
+        for (int i = tid; i < L * 128; i += NTC) sts32(sm + M::P_BIAS + i * 4, __float_as_uint(gbias[im.b_layer + (i >> 2) * 8 + (i & 3)]));
     }
     __syncthreads();
-    cluster_sync_all();                                    // both CTAs' barriers are initialised before anybody signals the peer
+    cluster_sync_all();                                    // every CTA's barriers are initialised before anybody signals a peer
 
     const int w = warp, g = lane >> 2, t4 = lane & 3;
     const int b0 = tile * TU + g, b1 = b0 + 8;
@@ -948,7 +972,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
     const int jw = w >> 1, hw = w & 1;
     const uint32_t xchg = (uint32_t)(jw * 512 + hw * 8) + lane16;
     auto release = [&](uint32_t bar) { __syncwarp(); if (lane == 0) mbar_arrive_a(bar); };
-    auto release_remote = [&](uint32_t local_bar) { __syncwarp(); if (lane == 0) mbar_arrive_remote(mapa_u32(local_bar, peer)); };
+    auto release_remote = [&](uint32_t local_bar, uint32_t rank) { __syncwarp(); if (lane == 0) mbar_arrive_remote(mapa_u32(local_bar, rank)); };
 
     if (is_chain) {
         // ===================================================================================== chain CTA
@@ -965,54 +989,33 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     }
             }
         } else {
-            const uint32_t cstride = (uint32_t)ntiles_alloc * 4096u, rstride = (uint32_t)ntiles_alloc * 2048u;
-            const unsigned char* gcond = static_cast<const unsigned char*>(p.Lh) + (size_t)tile * 4096 + (size_t)(w * 32 + lane) * 16;
+            const uint32_t rstride = (uint32_t)ntiles_alloc * 2048u;
             unsigned char* gring = static_cast<unsigned char*>(p.ring) + (size_t)tile * 2048;
             const int cw = 8 * w + 2 * t4;
             const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16, o_res = 16384u + (uint32_t)(w * 2) * 512 + lane16;
             const uint32_t r_hbuf = mapa_u32(sm + M::T_HBUF + xchg, 1);            // this thread's slot of the tail CTA's h tiles
             const uint32_t r_hfull = mapa_u32(s_hfull, 1);
             const uint32_t s_bias = sm + M::C_BIAS + (uint32_t)(w * 4 + t4) * 32;   // this thread's Bh / Bres pairs of layer 0 (+ 1 KB per layer)
-            const uint32_t s_cond = sm + M::C_COND + (uint32_t)(w * 32 + lane) * 16;  // this thread's 16 B of a conditioning tile (+ 4 KB per slot)
             const uint32_t s_ap = sm + M::C_AP + (uint32_t)(w * 32 + lane) * 32;    // this thread's 8 floats of a pre-activation tile (+ 8 KB per buffer)
-            // Conditioning of the step `itp` (three steps ahead of its use), no register and no scoreboard involved: every thread copies
-            // the 16 bytes it will read back itself (cp.async; completion = the thread's own cp.async group, no barrier) into a 4-slot ring.
-            int tp = t_begin, lp = 0;
-            uint32_t pcnt = 0;
-            const unsigned char* cptr = gcond + (size_t)t_begin * L * cstride;         // conditioning of step itp (steps are consecutive in memory)
-            auto stage_step = [&]() {
-                if (tp < t_end) cp_async16(s_cond + (pcnt & 3) * 4096, cptr);
-                cptr += cstride;
-                cp_async_commit();
-                pcnt++;
-                if (++lp == L) { lp = 0; tp++; }
-            };
             uint32_t xa[4][4];
             float accp[2][4];
             float2 brn = make_float2(0.f, 0.f);
             float xres[4] = {0.f, 0.f, 0.f, 0.f};
             int t1 = t_begin, l1 = 0;                          // the coming step (number pn)
             uint32_t pn = 0;
-            // accp <- (Bh + Lh) + [Wprev . x[t-d], from the tail CTA] of the coming step; everything it reads is in shared memory
+            // accp <- (Bh + Lh) + Wprev . x[t-d] of the coming step: computed by the prep CTA, read from this CTA's shared memory
             auto prep = [&](const bool ap_ok) {
                 if (t1 < t_end) {
-                    cp_async_wait_pending<1>();                // this thread's conditioning of that step has landed (the group of the step after may be in flight)
-                    const uint4 cb = lds128(s_cond + (pn & 3) * 4096);
-                    const uint4 bq = lds128(s_bias + l1 * 1024);
-                    const uint4 b2 = lds128(s_bias + l1 * 1024 + 16);
-                    if (!ap_ok) mbar_wait_a(s_apfull + 8 * (pn & 1), (pn >> 1) & 1);
-                    const uint4 a0 = lds128(s_ap + (pn & 1) * 8192), a1 = lds128(s_ap + (pn & 1) * 8192 + 16);
-                    const float4 bh = make_float4(__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z), __uint_as_float(bq.w));
+                    const uint2 b2 = lds64(s_bias + l1 * 1024 + 16);
+                    if (!ap_ok) mbar_wait_a(s_apfull + 8 * (pn & 3), (pn >> 2) & 1);
+                    const uint4 a0 = lds128(s_ap + (pn & 3) * 8192), a1 = lds128(s_ap + (pn & 3) * 8192 + 16);
                     brn = make_float2(__uint_as_float(b2.x), __uint_as_float(b2.y));
-                    const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
-                    accp[0][0] = (bh.x + c0.x) + __uint_as_float(a0.x); accp[0][1] = (bh.y + c0.y) + __uint_as_float(a0.y);
-                    accp[0][2] = (bh.x + c1.x) + __uint_as_float(a0.z); accp[0][3] = (bh.y + c1.y) + __uint_as_float(a0.w);
-                    accp[1][0] = (bh.z + c2.x) + __uint_as_float(a1.x); accp[1][1] = (bh.w + c2.y) + __uint_as_float(a1.y);
-                    accp[1][2] = (bh.z + c3.x) + __uint_as_float(a1.z); accp[1][3] = (bh.w + c3.y) + __uint_as_float(a1.w);
-                    // the tile has been read: arm its barrier for the tile after next (one thread, ordered before this warp's "free"
-                    // signal), then hand the buffer back to the tail CTA
-                    if (tid == 0) mbar_expect_a(s_apfull + 8 * (pn & 1), 8192);
-                    release_remote(s_apfree + 8 * (pn & 1));
+                    accp[0][0] = __uint_as_float(a0.x); accp[0][1] = __uint_as_float(a0.y); accp[0][2] = __uint_as_float(a0.z); accp[0][3] = __uint_as_float(a0.w);
+                    accp[1][0] = __uint_as_float(a1.x); accp[1][1] = __uint_as_float(a1.y); accp[1][2] = __uint_as_float(a1.z); accp[1][3] = __uint_as_float(a1.w);
+                    // the tile has been read: arm its barrier for the tile NAP steps on (one thread, ordered before this warp's "free"
+                    // signal), then hand the buffer back to the prep CTA
+                    if (tid == 0) mbar_expect_a(s_apfull + 8 * (pn & 3), 8192);
+                    release_remote(s_apfree + 8 * (pn & 3), 2);
                 }
                 pn++;
                 if (++l1 == L) { l1 = 0; t1++; }
@@ -1023,8 +1026,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                 sts32(sm + M::C_EPBUF + ((g + 8) * EROW + 4 * w + t4) * 4, ep[ys[TU + g + 8] * 32 + 4 * w + t4]);
             }
             StepIt it0{t_begin, 0, t_begin % slots};
-            stage_step(); stage_step(); stage_step();
-            prep(false);                                       // step 0 (its history half was shipped by the tail's prologue)
+            prep(false);                                       // step 0
             bar_compute();
 
             uint32_t pc = 0, epar = 0, hcnt = 0;               // ring piece counter, sample parity, h tiles handed over
@@ -1052,7 +1054,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     const uint32_t en = sm + M::C_EPBUF + (epar ^ 1) * (TU * EROW * 4);
                     cp_async4(en + (g * EROW + 4 * w + t4) * 4, ep + (size_t)yc0 * 128 + (4 * w + t4) * 4);
                     cp_async4(en + ((g + 8) * EROW + 4 * w + t4) * 4, ep + (size_t)yc1 * 128 + (4 * w + t4) * 4);
-                    // (no commit here: these two ride in the cp.async group of this sample's first layer step)
+                    cp_async_commit();                         // landed long before the next sample starts (waited for at the end of this one)
                 }
                 bar_compute();
 #pragma unroll
@@ -1109,13 +1111,13 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                         if (v0) { p.xtOut[((size_t)l * B + b0) * R + cw] = xres[0]; p.xtOut[((size_t)l * B + b0) * R + cw + 1] = xres[1]; }
                         if (v1) { p.xtOut[((size_t)l * B + b1) * R + cw] = xres[2]; p.xtOut[((size_t)l * B + b1) * R + cw + 1] = xres[3]; }
                     }
-                    stage_step();                              // conditioning of three steps ahead
                     {   // look at the coming step's barriers
                         const uint32_t npc = pc + 1;
-                        ok_f = mbar_try_a(s_full + 8 * (npc & 1), (npc >> 1) & 1);
-                        ok_ap = mbar_try_a(s_apfull + 8 * (pn & 1), (pn >> 1) & 1);
-                        ok_hf = mbar_try_a(s_hfree + 8 * (hcnt & 1), ((hcnt >> 1) & 1) ^ 1);
+                        ok_f = mbar_probe_a(s_full + 8 * (npc & 1), (npc >> 1) & 1);
+                        ok_ap = mbar_probe_a(s_apfull + 8 * (pn & 3), (pn >> 2) & 1);
+                        ok_hf = mbar_probe_a(s_hfree + 8 * (hcnt & 1), ((hcnt >> 1) & 1) ^ 1);
                     }
+                    TRACE2(0, 13);
                     if (l + 1 < L) {
                         bar_compute();
 #pragma unroll
@@ -1123,13 +1125,13 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     }
                     TRACE2(0, 11);
                 }
-                cp_async_wait_pending<3>();                    // the previous-index rows rode in this sample's first group: long landed
+                cp_async_wait_all();                           // the previous-index rows of the next sample
                 epar ^= 1;
                 if (++it0.slot == slots) it0.slot = 0;
                 it0.t++;
             }
         }
-    } else {
+    } else if (is_tail) {
         // ===================================================================================== tail CTA
         if (warp == NCW) {
             if (lane == 0) {
@@ -1142,11 +1144,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     pc++;
                 };
                 for (int t = t_begin; t < t_end; t++) {
-                    for (int l = 0; l < L; l++) {
-                        // Wprev of the layer two steps ahead lives in the block of the layer before it (lat_pack_kernel), then this step's Wskip
-                        put(img + (size_t)((l + 1) % L) * im.layer_bytes + C::W_PREV, 16384);
-                        put(img + (size_t)l * im.layer_bytes + C::W_SKIP, S * 128);
-                    }
+                    for (int l = 0; l < L; l++) put(img + (size_t)l * im.layer_bytes + C::W_SKIP, S * 128);
                     for (int q = 0; q < NQ; q++)
                         put(q < C::NQ_ZS ? img + im.off_zs + (size_t)q * C::ZS_PIECE : img + im.off_za + (size_t)(q - C::NQ_ZS) * C::ZA_PIECE,
                             q < C::NQ_ZS ? C::ZS_PIECE : C::ZA_PIECE);
@@ -1158,74 +1156,11 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
             float sk[C::NSK][4];
 #pragma unroll
             for (int i = 0; i < C::NSK; i++) sk[i][0] = sk[i][1] = sk[i][2] = sk[i][3] = 0.f;
-            // ---- the dilated-history half of the pre-activations, two steps ahead of the chain CTA
-            int* dil = reinterpret_cast<int*>(smem_raw + M::T_DIL);
-            const uint32_t rstride = (uint32_t)ntiles_alloc * 2048u;
-            const unsigned char* gring = static_cast<const unsigned char*>(p.ring) + (size_t)tile * 2048;
-            const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16;
-            const uint32_t r_ap = mapa_u32(sm + M::C_AP + (uint32_t)(w * 32 + lane) * 32, 0);   // this thread's 8 floats of the chain CTA's tiles
-            const uint32_t r_apfull = mapa_u32(s_apfull, 0);
-            auto advance = [&](StepIt& it) { if (++it.l == L) { it.l = 0; it.t++; if (++it.slot == slots) it.slot = 0; } };
-            // history tile x_l[t-d] of the step `itp` (zero before the start of the utterance, nv_wavenet.cuh:106): warps 0-3, 128 x 16 B,
-            // into a 4-slot ring, completion on an mbarrier (every warp reads the whole tile); staged two steps before its use
-            StepIt itp{t_begin, 0, t_begin % slots};
-            uint32_t pcnt = 0;
-            auto stage_history = [&]() {
-                if (w < 4) {
-                    const uint32_t slot4 = pcnt & 3;
-                    const int d = dil[itp.l];
-                    const uint32_t dst = sm + M::T_PST + slot4 * 2048 + (uint32_t)(w * 32 + lane) * 16;
-                    if (itp.t >= t_end || itp.t < d) {
-                        sts128(dst, make_uint4(0, 0, 0, 0));
-                        mbar_arrive_a(s_pfull + 8 * slot4);
-                    } else {
-                        int sl = itp.slot - d; if (sl < 0) sl += slots;
-                        cp_async16(dst, gring + (size_t)((uint32_t)(sl * L + itp.l) * rstride) + (size_t)(w * 32 + lane) * 16);
-                        cp_async_arrive_noinc(s_pfull + 8 * slot4);
-                    }
-                }
-                pcnt++;
-                advance(itp);
-            };
-            int t1 = t_begin, l1 = 0;                          // the step whose history half is computed next (number pn)
-            uint32_t pn = 0;
-            // Wprev . x[t-d] of step pn -> the chain CTA's pre-activation tile pn & 1 (free once the chain has read tile pn - 2)
-            auto prev_gemm = [&](const uint4 bt0, const uint4 bg0, const uint4 bt1, const uint4 bg1) {
-                if (t1 < t_end) {
-                    const uint32_t slot4 = pn & 3;
-                    mbar_wait_a(s_pfull + 8 * slot4, (pn >> 2) & 1);
-                    uint32_t pb[4][4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) load_a(pb[j], sm + M::T_PST + slot4 * 2048 + j * 512 + lane16);
-                    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
-                    hmma(a0, pb[0], bt0.x, bt0.y); hmma(a1, pb[0], bg0.x, bg0.y); hmma(u0, pb[2], bt1.x, bt1.y); hmma(u1, pb[2], bg1.x, bg1.y);
-                    hmma(a0, pb[1], bt0.z, bt0.w); hmma(a1, pb[1], bg0.z, bg0.w); hmma(u0, pb[3], bt1.z, bt1.w); hmma(u1, pb[3], bg1.z, bg1.w);
-                    mbar_wait_a(s_apfree + 8 * (pn & 1), ((pn >> 1) & 1) ^ 1);
-                    st_async_v4(r_ap + (pn & 1) * 8192, a0[0] + u0[0], a0[1] + u0[1], a0[2] + u0[2], a0[3] + u0[3], r_apfull + 8 * (pn & 1));
-                    st_async_v4(r_ap + (pn & 1) * 8192 + 16, a1[0] + u1[0], a1[1] + u1[1], a1[2] + u1[2], a1[3] + u1[3], r_apfull + 8 * (pn & 1));
-                }
-                pn++;
-                if (++l1 == L) { l1 = 0; t1++; }
-            };
-            stage_history(); stage_history(); stage_history(); stage_history();
-            for (int k = 0; k < 2; k++) {                      // prologue: steps 0 and 1, weights straight from the image
-                const unsigned char* gp = img + (size_t)((k + L - 1) % L) * im.layer_bytes + C::W_PREV;
-                prev_gemm(ldg_nc_v4(gp + o_t0), ldg_nc_v4(gp + o_g0), ldg_nc_v4(gp + o_t0 + 512), ldg_nc_v4(gp + o_g0 + 512));
-            }
             uint32_t pc = 0, hcnt = 0;
             for (int t = t_begin; t < t_end; t++) {
                 const float sel0 = (2 * w + 0 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w] : 0.5f;
                 const float sel1 = (2 * w + 1 + tile * TU) < B ? p.sel[(size_t)t * B + tile * TU + 2 * w + 1] : 0.5f;
                 for (int l = 0; l < L; l++, pc++, hcnt++) {
-                    {   // off the chain: the history half of the step after next, then the staging of the tile four steps ahead
-                        const uint32_t sa = pc & 3, pa = sm + M::T_RING + sa * M::SLOT1;
-                        mbar_wait_a(s_full + 8 * sa, (pc >> 2) & 1);
-                        const uint4 bt0 = lds128(pa + o_t0), bg0 = lds128(pa + o_g0), bt1 = lds128(pa + o_t0 + 512), bg1 = lds128(pa + o_g0 + 512);
-                        prev_gemm(bt0, bg0, bt1, bg1);
-                        release(s_empty + 8 * sa);
-                        pc++;
-                        stage_history();
-                    }
                     const uint32_t hb = sm + M::T_HBUF + (hcnt & 1) * 2048;
                     mbar_wait_a(s_hfull + 8 * (hcnt & 1), (hcnt >> 1) & 1);
                     TRACE2(1, 16);
@@ -1247,7 +1182,7 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
                     // the h tile has been read (the HMMAs above hold its values): arm its barrier for the tile after next (one thread,
                     // ordered before this warp's "free" signal), then hand the buffer back to the chain CTA
                     if (tid == 0) mbar_expect_a(s_hfull + 8 * (hcnt & 1), 2048);
-                    release_remote(s_hfree + 8 * (hcnt & 1));
+                    release_remote(s_hfree + 8 * (hcnt & 1), 0);
                     release(s_empty + 8 * sl);
                     TRACE2(1, 15);
                     if (DUMP) {
@@ -1398,6 +1333,90 @@ __global__ void __launch_bounds__(NTC, 1) wn_lat2_kernel(const WnParams p, const
             }
             if (tid < TU && tile * TU + tid < B) { p.yCur[tile * TU + tid] = ys[tid]; p.yPrev[tile * TU + tid] = ys[TU + tid]; }
         }
+    } else {
+        // ===================================================================================== prep CTA
+        // (Bh + Lh) + Wprev . x[t-d] of every step, as far ahead of the chain CTA as its NAP tile buffers allow.  Nothing here depends on
+        // the current sample: the history it reads was written by the chain CTA at least L - 9 steps earlier (wn_launch_lat asks for L >= 12).
+        const int nsteps = p.count * L;
+        if (warp == NCW) {
+            if (lane == 0) {
+                int l = 0;
+                for (int n = 0; n < nsteps; n++) {
+                    const uint32_t sl = n & 3;
+                    mbar_wait_a(s_empty + 8 * sl, ((n >> 2) & 1) ^ 1);
+                    mbar_expect_a(s_full + 8 * sl, 16384);
+                    // Wprev of layer l lives in the block of the layer before it (lat_pack_kernel)
+                    tma_load_a(sm + M::P_RING + sl * 16384, img + (size_t)((l + L - 1) % L) * im.layer_bytes + C::W_PREV, 16384, s_full + 8 * sl);
+                    if (++l == L) l = 0;
+                }
+            }
+        } else {
+            int* dil = reinterpret_cast<int*>(smem_raw + M::P_DIL);
+            const uint32_t rstride = (uint32_t)ntiles_alloc * 2048u, cstride = (uint32_t)ntiles_alloc * 4096u;
+            const unsigned char* gring = static_cast<const unsigned char*>(p.ring) + (size_t)tile * 2048;
+            const uint32_t o_t0 = (uint32_t)(w * 2) * 512 + lane16, o_g0 = (uint32_t)((8 + w) * 2) * 512 + lane16;
+            const uint32_t r_ap = mapa_u32(sm + M::C_AP + (uint32_t)(w * 32 + lane) * 32, 0);   // this thread's 8 floats of the chain CTA's tiles
+            const uint32_t r_apfull = mapa_u32(s_apfull, 0);
+            const uint32_t s_cond = sm + M::P_COND + (uint32_t)(w * 32 + lane) * 16;  // this thread's 16 B of a conditioning tile (+ 4 KB per slot)
+            const uint32_t s_bias = sm + M::P_BIAS + (uint32_t)(w * 4 + t4) * 16;     // this thread's Bh of layer 0 (+ 512 B per layer)
+            // Staging of the step `itp`, three steps before its use, no register and no scoreboard involved:
+            //  * its conditioning tile: every thread copies the 16 bytes it will read back itself (cp.async; completion = the thread's
+            //    own cp.async group, no barrier);
+            //  * its dilated history x_l[t-d] (zero before the start of the utterance, nv_wavenet.cuh:106): warps 0-3, 128 x 16 B,
+            //    completion on an mbarrier (every warp reads the whole tile).
+            // NPS = 8 slots: a slot is staged again five steps after its use, and the weight ring (4 pieces) keeps the warps within four.
+            StepIt itp{t_begin, 0, t_begin % slots};
+            uint32_t pcnt = 0;
+            const unsigned char* cptr = static_cast<const unsigned char*>(p.Lh) + (size_t)tile * 4096 + (size_t)(w * 32 + lane) * 16 + (size_t)t_begin * L * cstride;
+            auto stage = [&]() {
+                const uint32_t slot = pcnt & (M::NPS - 1);
+                if (itp.t < t_end) cp_async16(s_cond + slot * 4096, cptr);
+                cptr += cstride;
+                if (w < 4) {
+                    const int d = dil[itp.l];
+                    const uint32_t dst = sm + M::P_PST + slot * 2048 + (uint32_t)(w * 32 + lane) * 16;
+                    if (itp.t >= t_end || itp.t < d) {
+                        sts128(dst, make_uint4(0, 0, 0, 0));
+                        mbar_arrive_a(s_pfull + 8 * slot);
+                    } else {
+                        int sl = itp.slot - d; if (sl < 0) sl += slots;
+                        cp_async16(dst, gring + (size_t)((uint32_t)(sl * L + itp.l) * rstride) + (size_t)(w * 32 + lane) * 16);
+                        cp_async_arrive_noinc(s_pfull + 8 * slot);
+                    }
+                }
+                cp_async_commit();
+                pcnt++;
+                if (++itp.l == L) { itp.l = 0; itp.t++; if (++itp.slot == slots) itp.slot = 0; }
+            };
+            stage(); stage(); stage();
+            int l1 = 0;
+            for (int n = 0; n < nsteps; n++) {
+                const uint32_t sl = n & 3, pa = sm + M::P_RING + sl * 16384, slot = n & (M::NPS - 1), buf = n & (M::NAP - 1);
+                cp_async_wait_pending<2>();                    // this thread's conditioning of step n has landed (two later groups may be in flight)
+                const uint4 cb = lds128(s_cond + slot * 4096);
+                const uint4 bq = lds128(s_bias + l1 * 512);
+                mbar_wait_a(s_full + 8 * sl, (n >> 2) & 1);
+                const uint4 bt0 = lds128(pa + o_t0), bg0 = lds128(pa + o_g0), bt1 = lds128(pa + o_t0 + 512), bg1 = lds128(pa + o_g0 + 512);
+                mbar_wait_a(s_pfull + 8 * slot, (n >> 3) & 1);
+                uint32_t pb[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) load_a(pb[j], sm + M::P_PST + slot * 2048 + j * 512 + lane16);
+                const float4 bh = make_float4(__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z), __uint_as_float(bq.w));
+                const float2 c0 = unpack_h2(cb.x), c1 = unpack_h2(cb.y), c2 = unpack_h2(cb.z), c3 = unpack_h2(cb.w);
+                float a0[4] = {bh.x + c0.x, bh.y + c0.y, bh.x + c1.x, bh.y + c1.y}, a1[4] = {bh.z + c2.x, bh.w + c2.y, bh.z + c3.x, bh.w + c3.y};
+                float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
+                hmma(a0, pb[0], bt0.x, bt0.y); hmma(a1, pb[0], bg0.x, bg0.y); hmma(u0, pb[2], bt1.x, bt1.y); hmma(u1, pb[2], bg1.x, bg1.y);
+                hmma(a0, pb[1], bt0.z, bt0.w); hmma(a1, pb[1], bg0.z, bg0.w); hmma(u0, pb[3], bt1.z, bt1.w); hmma(u1, pb[3], bg1.z, bg1.w);
+                release(s_empty + 8 * sl);
+                // the chain CTA's tile buffer n % NAP is free once it has read tile n - NAP
+                mbar_wait_a(s_apfree + 8 * buf, ((n / M::NAP) & 1) ^ 1);
+                st_async_v4(r_ap + buf * 8192, a0[0] + u0[0], a0[1] + u0[1], a0[2] + u0[2], a0[3] + u0[3], r_apfull + 8 * buf);
+                st_async_v4(r_ap + buf * 8192 + 16, a1[0] + u1[0], a1[1] + u1[1], a1[2] + u1[2], a1[3] + u1[3], r_apfull + 8 * buf);
+                stage();
+                if (++l1 == L) l1 = 0;
+            }
+            cp_async_wait_all();
+        }
     }
 #undef TRACE2
     // nobody leaves while the peer may still write into this CTA's shared memory or arrive on its barriers
@@ -1473,7 +1492,7 @@ static cudaError_t lat_launch_S(const WnParams& p, const unsigned char* im8, int
     return cudaSuccess;
 }
 
-// the two-CTA cluster variant: grid = 2 x tiles, cluster (2, 1, 1)
+// the cluster variant: grid = NCL x tiles, cluster (NCL, 1, 1)
 template <int S, bool DUMP, bool TRC>
 static cudaError_t lat2_go(const WnParams& pp, const unsigned char* im8, int tiles, int ntiles_alloc, cudaStream_t stream)
 {
@@ -1481,13 +1500,13 @@ static cudaError_t lat2_go(const WnParams& pp, const unsigned char* im8, int til
     cudaError_t e = cudaFuncSetAttribute(wn_lat2_kernel<S, DUMP, TRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * tiles, 1, 1);
+    cfg.gridDim = dim3(NCL * tiles, 1, 1);
     cfg.blockDim = dim3(NTC, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = NCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, wn_lat2_kernel<S, DUMP, TRC>, pp, im8, ntiles_alloc);
@@ -1505,20 +1524,20 @@ static cudaError_t lat2_launch_S(const WnParams& p, const unsigned char* im8, in
     return e;
 }
 
-// cluster: serve every 16-utterance tile with a cluster of two CTAs (chain / tail) instead of one
+// cluster: serve every 16-utterance tile with a cluster of three CTAs (chain / tail / prep) instead of one
 cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, bool cluster, cudaStream_t stream, WnLaunchInfo* info)
 {
     const int grid = wn_lat_tiles(p.B), ntiles_alloc = wn_lat_tiles(engine_B);
     const unsigned char* im8 = static_cast<const unsigned char*>(image);
     size_t smem = 0;
     cudaError_t e;
-    // the cluster kernel's tail CTA reads history tiles the chain CTA wrote at least L - 5 steps earlier: it wants a few steps of margin
-    if (cluster && p.L >= 8) {
+    // the cluster kernel's prep CTA reads history tiles the chain CTA wrote at least L - 9 steps earlier: it wants a few steps of margin
+    if (cluster && p.L >= 12 && NCL * grid <= 148) {
         if (p.S == 256) e = lat2_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);
         else if (p.S == 128) e = lat2_launch_S<128>(p, im8, grid, ntiles_alloc, stream, &smem);
         else return cudaErrorInvalidValue;
         if (e != cudaSuccess) return e;
-        if (info) { info->kernel = 18; info->grid = 2 * grid; info->block = NTC; info->smem_bytes = (int)smem; info->batch_per_cta = TU; info->cluster = 2; }
+        if (info) { info->kernel = 18; info->grid = NCL * grid; info->block = NTC; info->smem_bytes = (int)smem; info->batch_per_cta = TU; info->cluster = NCL; }
         return cudaGetLastError();
     }
     if (p.S == 256) e = lat_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);

@@ -243,7 +243,7 @@ def _check_sampled_index(p, sel, y):
     (64, 256, 256, 20, 64, 12, 4),
     (64, 256, 256, 20, 130, 6, 2),        # several batch tiles, the last one nearly empty
     (64, 256, 256, 5, 100, 10, 16),       # odd layer count, partially filled tile
-    (64, 256, 256, 8, 20, 30, 4),         # the shortest stack the two-CTA cluster kernel takes
+    (64, 256, 256, 12, 20, 30, 4),        # the shortest stack the cluster kernel takes
 ])
 def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
     R, S, A, L, B, N, md = shape
@@ -262,7 +262,7 @@ def test_fp16_logits_teacher_forced(shape, kernel, monkeypatch):
         e.run(n_run, B, y, dump_activations=True); e.synchronize()
         assert e.launch_info()["kernel"] == {"stream": 16, "lat": 18, "lat_single": 18}.get(kernel, 17)
         if kernel.startswith("lat"):
-            assert e.launch_info()["cluster"] == (2 if kernel == "lat" and L >= 8 else 1)      # shorter stacks: single-CTA kernel
+            assert e.launch_info()["cluster"] == (3 if kernel == "lat" and L >= 12 else 1)     # shorter stacks: single-CTA kernel
         o16 = cpu_oracle(wn_, L, B, n_run, R, S, A, md, prec=po.PREC_FP16); o16.set_forced(f); o16.run(n_run, B)
         o = cpu_oracle(wn_, L, B, n_run, R, S, A, md); o.set_forced(f); o.run(n_run, B)
         ag = e.activations()

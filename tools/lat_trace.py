@@ -27,8 +27,8 @@ assert lib.nvwn_debug_trace(e._h, T, None, 0) == 0
 e.run(N, B, None); torch.cuda.synchronize()
 buf = np.zeros(3 * 1024, np.uint64)
 assert lib.nvwn_debug_trace(e._h, T, buf.ctypes.data, 1) == 0
-names = {1: "sample start (ys read)", 2: "x0 built", 10: "h exchanged", 11: "layer done (x exchanged)", 12: "cur+prev GEMM issued", 13: "gate done",
-         14: "res done", 15: "skip issued", 16: "tail: h seen", 17: "bg: step start", 20: "relu(skip) exchanged", 21: "relu(Zs) exchanged", 22: "logits exchanged", 23: "sample done"}
+names = {1: "sample start (ys read)", 2: "x0 built", 10: "h exchanged", 11: "layer done (x exchanged)", 12: "cur+prev GEMM issued", 13: "probes issued",
+         14: "res done", 15: "skip issued", 16: "tail: h seen", 17: "tail: prev part starts", 18: "tail: pre-activation shipped", 20: "relu(skip) exchanged", 21: "relu(Zs) exchanged", 22: "logits exchanged", 23: "sample done"}
 ev = []
 for role in range(3):
     for v in buf[role * 1024:(role + 1) * 1024]:
