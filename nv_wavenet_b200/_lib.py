@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libwavenet_infer.so")
+LIB_PATH = os.environ.get("NVWN_LIB_PATH") or os.path.join(HERE, "lib", "libwavenet_infer.so")      # (override: experimental builds)
 
 FP32, FP16, FP32_FAST = 0, 1, 2
 KERNEL_AUTO, KERNEL_STREAM, KERNEL_TENSORCORE, KERNEL_LATENCY = 0, 16, 17, 18

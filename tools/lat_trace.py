@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, ".")
 import os
 os.environ.setdefault("NVWN_FP16_KERNEL", "lat")
-# NVWN_LAT_CLUSTER=0 traces the single-CTA kernel; default: the cluster kernel (role 0 = chain CTA, role 1 = tail CTA)
+# NVWN_LAT_CLUSTER=0 traces the single-CTA kernel; default: the cluster kernel (role 0 = chain CTA, role 1 = tail CTA; the prep CTA is not traced)
 import nv_wavenet_b200 as nw
 from nv_wavenet_b200 import _lib
 from tests import refgen
