@@ -16,7 +16,7 @@
 //
 // Replaces nv_wavenet_persistent.cuh + matrix_math.cuh + softmax.cuh of the reference for T_data = half.
 // Numerical contract (oracle/wavenet_oracle.c, WNO_PREC_FP16): weights, biases, embeddings, Lh and every GEMM
-// input rounded to fp16; fp32 accumulation; residual stream, skip sum, softmax in fp32.  The fused schedule folds
+// input rounded to fp16; fp32 accumulation; residual stream, skip sum, softmax in fp32 (logits parked as fp16 offsets from the row max).  The fused schedule folds
 // Wcur_l . Wres_{l-1} into one fp16 matrix (see the kernel) -- same tolerance, checked by the same tests.
 #include "wn_common.h"
 #include "wn_math.cuh"
@@ -1063,8 +1063,9 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             if (tid == tr_tid) TRACE(0, 9);
 
             // ---------------- Za, softmax, categorical sample   (reference.cpp:100-121)
-            // The two threads of an utterance each take 128 logits: one TMEM pass parks them as fp16 in the thread's own row
-            // of the (now dead) activation tiles and finds the local max; exp / sums / scan run from shared memory; the
+            // The two threads of an utterance each take 128 logits: a first TMEM pass finds the local max in fp32, a second one parks
+            // (z - max) as fp16 in the thread's own row of the (now dead) activation tiles -- the rounding error is proportional to the
+            // distance from the max, i.e. negligible where the probability mass is; exp / sums / scan run from shared memory; the
             // halves meet through s_pair (local max, local sum) and s_y.
             mbar_wait(out_full, ph_out); ph_out ^= 1;
             tc_fence_after_sync();
@@ -1074,13 +1075,24 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
             float mx = 0.f;                                             // matrix.cpp:171 starts the max at 0
             float csum[NCH];
             float lsum = 0.f;
-            float mxs = 0.f;
-            auto expz = [&](uint32_t packed, float& e0, float& e1) {
+            auto expz = [&](uint32_t packed, float& e0, float& e1) {       // packed = (z - local max) in fp16
                 const float2 z = unpack_h2(packed);
-                e0 = wn::exp2f_fast(fmaf(z.x, 1.4426950408889634f, -mxs));
-                e1 = wn::exp2f_fast(fmaf(z.y, 1.4426950408889634f, -mxs));
+                e0 = wn::exp2f_fast(z.x * 1.4426950408889634f);
+                e1 = wn::exp2f_fast(z.y * 1.4426950408889634f);
             };
             if (wv) {
+#pragma unroll 1
+                for (int c0 = a_lo; c0 < a_lo + PART; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(DZA + lane_off + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float z0 = __uint_as_float(v[j]) + s_bza[c0 + j], z1 = __uint_as_float(v[j + 1]) + s_bza[c0 + j + 1];
+                        mx = fmaxf(mx, fmaxf(z0, z1));
+                        if (dump && valid) { p.Za[(size_t)b * A + c0 + j] = z0; p.Za[(size_t)b * A + c0 + j + 1] = z1; }
+                    }
+                }
 #pragma unroll 1
                 for (int c0 = a_lo; c0 < a_lo + PART; c0 += 32) {
                     uint32_t v[32];
@@ -1090,9 +1102,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         const float z0 = __uint_as_float(v[j]) + s_bza[c0 + j], z1 = __uint_as_float(v[j + 1]) + s_bza[c0 + j + 1];
-                        mx = fmaxf(mx, fmaxf(z0, z1));
-                        o[j >> 1] = pack_h2(z0, z1);
-                        if (dump && valid) { p.Za[(size_t)b * A + c0 + j] = z0; p.Za[(size_t)b * A + c0 + j + 1] = z1; }
+                        o[j >> 1] = pack_h2(z0 - mx, z1 - mx);
                     }
                     unsigned char* kt = t_big + (size_t)(c0 >> 6) * TILE;      // scratch: own row only
                     const int q = (c0 & 63) >> 3;
@@ -1100,7 +1110,6 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     for (int i = 0; i < 4; i++)
                         *reinterpret_cast<uint4*>(kt + chunk_off(row, q + i)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                 }
-                mxs = mx * 1.4426950408889634f;
 #pragma unroll
                 for (int c = 0; c < NCH; c++) {
                     const int c0 = a_lo + 16 * c;
@@ -1174,7 +1183,7 @@ __global__ void __launch_bounds__(NT, 1) wn_tc_kernel(const WnParams p, const un
                     for (int a = a_lo; a < a_lo + PART; a++) {
                         const unsigned char* kt = t_big + (size_t)(a >> 6) * TILE;
                         const float z = __half2float(*reinterpret_cast<const __half*>(kt + chunk_off(row, (a & 63) >> 3) + (a & 7) * 2));
-                        p.P[(size_t)b * A + a] = wn::exp2f_fast(fmaf(z, 1.4426950408889634f, -mxs)) * inv;
+                        p.P[(size_t)b * A + a] = wn::exp2f_fast(z * 1.4426950408889634f) * inv;
                     }
                 }
             }
