@@ -450,18 +450,21 @@ def run_ours(args, rank, world, local_rank):
     achieved = B * N * alg / (kernel_ms * 1e-3) / 1e9                # one launch = one step of one GPU
     # DRAM traffic is not measured on this run: the committed ncu capture (profiles/ncu_summary.json) gives bytes per unit
     # for a shorter launch of the same kernel; the figure scaled to this launch is reported as an extrapolation
+    kname = {16: "wn_stream_kernel", 17: "wn_tc_kernel", 18: "wn_lat2_kernel" if info["cluster"] > 1 else "wn_lat_kernel"}.get(info["kernel"], str(info["kernel"]))
+    traffic = None                                  # DRAM bytes of one launch of this very shape, if the committed ncu capture is of it
     traffic_x = None
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof):
         try:
             pj = json.load(open(prof))
             if pj.get("config") == args.config and pj.get("kernel_id") == info["kernel"] and kname in pj.get("kernel", ""):
+                if pj.get("capture_samples") == N and pj.get("capture_batch") == B:
+                    traffic = pj["dram_bytes_read"] + pj["dram_bytes_write"]
                 traffic_x = {"value": pj["dram_bytes_per_unit"] * B * N, "dram_bytes_per_unit": pj["dram_bytes_per_unit"],
                              "capture_samples": pj.get("capture_samples"), "capture_batch": pj.get("capture_batch"), "source": "profiles/ncu_summary.json"}
         except Exception:
             traffic_x = None
-    kname = {16: "wn_stream_kernel", 17: "wn_tc_kernel", 18: "wn_lat2_kernel" if info["cluster"] > 1 else "wn_lat_kernel"}.get(info["kernel"], str(info["kernel"]))
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_extrapolated": traffic_x, "peak_source": peak_src, "kernel": kname,
                 "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_unit": alg, "units_per_launch": B * N,
                 "note": "BASELINE.md §2 normalisation: one read of all weights per utterance-sample; weights are re-used across the batch "

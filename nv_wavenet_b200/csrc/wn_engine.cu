@@ -42,6 +42,7 @@ cudaError_t wn_lat_pack(void* image, const WnParams& p, cudaStream_t stream);
 cudaError_t wn_lat_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int L, int B, cudaStream_t stream);
 cudaError_t wn_tc_cond_readback(float* dst_dev, const void* store, int first_sample, int nsamples, int TU, int L, int B, cudaStream_t stream);
 cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, bool cluster, cudaStream_t stream, WnLaunchInfo* info);
+int wn_lat_max_clusters(int S);
 
 namespace {
 
@@ -648,6 +649,9 @@ int nvwn_debug_trace(nvwn_engine* e, int t, unsigned long long* out_host, int fe
     CK(cudaMemcpy(out_host, e->trace, 3 * 1024 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
+
+// debug only: how many three-CTA clusters of the latency kernel the device runs at once (batches up to 16 x this use it)
+int nvwn_debug_lat_max_clusters(int S) { return wn_lat_max_clusters(S); }
 
 int nvwn_get_launch_info(nvwn_engine* e, nvwn_launch_info* info)
 {

@@ -1512,6 +1512,27 @@ static cudaError_t lat2_go(const WnParams& pp, const unsigned char* im8, int til
     e = cudaLaunchKernelEx(&cfg, wn_lat2_kernel<S, DUMP, TRC>, pp, im8, ntiles_alloc);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
+// how many clusters the device runs at once (a cluster needs NCL SMs of one GPC: fewer than 148 / NCL fit); 0 if the query fails
+template <int S>
+static int lat2_max_clusters()
+{
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    const size_t smem = CfgC<S>::SMEM;
+    if (cudaFuncSetAttribute(wn_lat2_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return cached = 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(NCL * 48, 1, 1);
+    cfg.blockDim = dim3(NTC, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = NCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, wn_lat2_kernel<S, false, false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    return cached = n;
+}
 template <int S>
 static cudaError_t lat2_launch_S(const WnParams& p, const unsigned char* im8, int tiles, int ntiles_alloc, cudaStream_t stream, size_t* smem_out)
 {
@@ -1524,6 +1545,8 @@ static cudaError_t lat2_launch_S(const WnParams& p, const unsigned char* im8, in
     return e;
 }
 
+int wn_lat_max_clusters(int S) { return S == 256 ? lat2_max_clusters<256>() : S == 128 ? lat2_max_clusters<128>() : 0; }
+
 // cluster: serve every 16-utterance tile with a cluster of three CTAs (chain / tail / prep) instead of one
 cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, bool cluster, cudaStream_t stream, WnLaunchInfo* info)
 {
@@ -1532,7 +1555,8 @@ cudaError_t wn_launch_lat(const WnParams& p, const void* image, int engine_B, bo
     size_t smem = 0;
     cudaError_t e;
     // the cluster kernel's prep CTA reads history tiles the chain CTA wrote at least L - 9 steps earlier: it wants a few steps of margin
-    if (cluster && p.L >= 12 && NCL * grid <= 148) {
+    const int fit = cluster ? wn_lat_max_clusters(p.S) : 0;
+    if (cluster && p.L >= 12 && grid <= fit) {               // every cluster must be resident at once: a second wave would halve the rate
         if (p.S == 256) e = lat2_launch_S<256>(p, im8, grid, ntiles_alloc, stream, &smem);
         else if (p.S == 128) e = lat2_launch_S<128>(p, im8, grid, ntiles_alloc, stream, &smem);
         else return cudaErrorInvalidValue;
