@@ -66,6 +66,15 @@ int nvwn_libc_selectors(float* selectors, int batch_size, int sample_count);
 int nvwn_set_conditioning_from_features(nvwn_engine* e, const float* features, int n_cond_channels, int num_frames,
                                         const float* upsample_weight, const float* upsample_bias, int window, int stride,
                                         const float* cond_weight, const float* cond_bias, int first_sample, void* stream);
+/* The same in two steps, for producers that run concurrently with generation: _load copies the features and the two layers' weights
+ * into engine-owned device memory (returns when the sources may be released); _run fills conditioning for samples
+ * [sample_begin, sample_begin + sample_count) of the loaded sequence, stored from engine sample first_sample + sample_begin,
+ * asynchronously on `stream` (order it before the nvwn_run_partial that consumes those samples with an event; successive _run
+ * calls must be on one stream or ordered by the caller: they share scratch). */
+int nvwn_cond_producer_load(nvwn_engine* e, const float* features, int n_cond_channels, int num_frames,
+                            const float* upsample_weight, const float* upsample_bias, int window, int stride,
+                            const float* cond_weight, const float* cond_bias, void* stream);
+int nvwn_cond_producer_run(nvwn_engine* e, int first_sample, int sample_begin, int sample_count, void* stream);
 /* The same arithmetic on the host (needs no GPU; test / reference use): Lh [T*stride][L][B][2R], host pointers. */
 int nvwn_cond_from_features_host(float* Lh, const float* features, int batch_size, int n_cond_channels, int num_frames,
                                  const float* upsample_weight, const float* upsample_bias, int window, int stride,

@@ -43,6 +43,8 @@ SYMBOLS = {
     "nvwn_get_audio": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "nvwn_mulaw_table": (C.c_int, [C.c_int, _vp, _vp, _vp]),
     "nvwn_set_conditioning_from_features": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "nvwn_cond_producer_load": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "nvwn_cond_producer_run": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "nvwn_cond_from_features_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int]),
     "nvwn_get_xt_out": (C.c_int, [_vp, C.c_int, _vp]),
     "nvwn_get_skip_out": (C.c_int, [_vp, C.c_int, _vp]),

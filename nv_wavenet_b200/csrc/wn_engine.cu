@@ -100,6 +100,11 @@ struct nvwn_engine {
     bool lat_cluster = true;                 // latency mode: a three-CTA cluster per tile while 3 x tiles fit one wave (NVWN_LAT_CLUSTER=0 disables; read once)
     bool lat_mode = false;                   // decided once at creation: latency-mode kernel (fragment-ordered layouts); tc_image holds its weight image
 
+    // conditioning producer (nvwn_cond_producer_load / _run): features | Wu | WuT | bu | Wc | bc | U chunk | Lh chunk in one allocation
+    float* cp_scratch = nullptr;
+    size_t cp_floats = 0;
+    int cp_C = 0, cp_T = 0, cp_K = 0, cp_stride = 0, cp_chunk = 0;
+
     float* lut_f = nullptr;                  // mu-law decode tables (nvwn_get_audio): A floats, then 2 x A int16 (wrap / saturate)
     unsigned long long* trace = nullptr;     // debug timeline (nvwn_debug_trace)
     int trace_t = -1;
@@ -286,7 +291,7 @@ int nvwn_destroy(nvwn_engine* e)
 {
     if (!e) return 0;
     void* ptrs[] = {e->blob, e->Lh, e->sel, e->forced, e->yPrev, e->yCur, e->yOut, e->ring, e->xtOut, e->skipOut,
-                    e->Zs, e->Za, e->P, e->stage_dev, e->tc_image, e->trace, e->lut_f};
+                    e->Zs, e->Za, e->P, e->stage_dev, e->tc_image, e->trace, e->lut_f, e->cp_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete e;
     return 0;
@@ -347,42 +352,76 @@ int nvwn_cond_from_features_host(float* Lh, const float* features, int batch_siz
     return 0;
 }
 
-int nvwn_set_conditioning_from_features(nvwn_engine* e, const float* features, int n_cond_channels, int num_frames,
-                                        const float* upsample_weight, const float* upsample_bias, int window, int stride,
-                                        const float* cond_weight, const float* cond_bias, int first_sample, void* stream)
+int nvwn_cond_producer_load(nvwn_engine* e, const float* features, int n_cond_channels, int num_frames,
+                            const float* upsample_weight, const float* upsample_bias, int window, int stride,
+                            const float* cond_weight, const float* cond_bias, void* stream)
 {
-    if (!e || !features || !upsample_weight || !upsample_bias || !cond_weight || !cond_bias) return fail(NVWN_EINVAL, "nvwn_set_conditioning_from_features: NULL argument");
+    if (!e || !features || !upsample_weight || !upsample_bias || !cond_weight || !cond_bias) return fail(NVWN_EINVAL, "nvwn_cond_producer_load: NULL argument");
     const int C = n_cond_channels, T = num_frames, K = window;
-    if (C < 1 || T < 1 || stride < 1 || K < stride) return fail(NVWN_EINVAL, "nvwn_set_conditioning_from_features: bad sizes (need window >= stride >= 1)");
-    const long long Nn = (long long)T * stride;
-    if (first_sample < 0 || first_sample + Nn > e->N) return fail(NVWN_EINVAL, "nvwn_set_conditioning_from_features: num_frames * stride samples do not fit the engine");
+    if (C < 1 || T < 1 || stride < 1 || K < stride) return fail(NVWN_EINVAL, "nvwn_cond_producer_load: bad sizes (need window >= stride >= 1)");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t per = (size_t)e->L * e->B * 2 * e->R;                       // floats of conditioning per sample
-    // chunk of whole samples: ~64 MB of fp32 at a time
-    int chunk = (int)(((size_t)16 << 20) / per);
+    int chunk = (int)(((size_t)16 << 20) / per);                             // chunk of whole samples: ~64 MB of fp32 at a time
     if (chunk < 1) chunk = 1;
-    if (chunk > Nn) chunk = (int)Nn;
     const size_t n_feat = (size_t)e->B * C * T, n_wu = (size_t)C * C * K, n_wc = (size_t)e->L * 2 * e->R * C, n_bc = (size_t)e->L * 2 * e->R;
-    // one scratch allocation: features | Wu | WuT | bu | Wc | bc | U chunk | Lh chunk
-    const size_t floats = n_feat + 2 * n_wu + C + n_wc + n_bc + (size_t)e->B * chunk * C + (size_t)chunk * per;
-    float* scratch = nullptr;
-    CK(cudaMalloc((void**)&scratch, floats * sizeof(float)));
-    float* d_feat = scratch; float* d_wu = d_feat + n_feat; float* d_wut = d_wu + n_wu; float* d_bu = d_wut + n_wu;
-    float* d_wc = d_bu + C; float* d_bc = d_wc + n_wc; float* d_u = d_bc + n_bc; float* d_out = d_u + (size_t)e->B * chunk * C;
+    const size_t floats = n_feat + 2 * n_wu + C + n_wc + n_bc + (size_t)e->B * chunk * C + (size_t)chunk * per + 16;
+    if (floats > e->cp_floats) {
+        if (e->cp_scratch) { CK(cudaDeviceSynchronize()); cudaFree(e->cp_scratch); e->cp_scratch = nullptr; e->cp_floats = 0; }
+        CK(cudaMalloc((void**)&e->cp_scratch, floats * sizeof(float)));
+        e->cp_floats = floats;
+    }
+    e->cp_C = C; e->cp_T = T; e->cp_K = K; e->cp_stride = stride; e->cp_chunk = chunk;
+    float* d_feat = e->cp_scratch; float* d_wu = d_feat + n_feat; float* d_wut = d_wu + n_wu; float* d_bu = d_wut + n_wu;
+    float* d_wc = d_bu + C; float* d_bc = d_wc + n_wc;
     cudaError_t ce = cudaSuccess;
     auto put = [&](float* dst, const float* src, size_t n) { if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDefault, st); };
     put(d_feat, features, n_feat); put(d_wu, upsample_weight, n_wu); put(d_bu, upsample_bias, C); put(d_wc, cond_weight, n_wc); put(d_bc, cond_bias, n_bc);
     if (ce == cudaSuccess) ce = wn_cond_transpose_wu(d_wut, d_wu, C, K, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);                   // host sources may be released by the caller now
+    if (ce != cudaSuccess) return fail((int)ce, std::string("nvwn_cond_producer_load: ") + cudaGetErrorString(ce));
+    return 0;
+}
+
+int nvwn_cond_producer_run(nvwn_engine* e, int first_sample, int sample_begin, int sample_count, void* stream)
+{
+    if (!e) return fail(NVWN_EINVAL, "nvwn_cond_producer_run: NULL engine");
+    if (!e->cp_scratch || e->cp_T < 1) return fail(NVWN_EINVAL, "nvwn_cond_producer_run: nvwn_cond_producer_load has not been called");
+    const int C = e->cp_C, T = e->cp_T, K = e->cp_K, stride = e->cp_stride, chunk = e->cp_chunk;
+    const long long Nn = (long long)T * stride;
+    if (sample_begin < 0 || sample_count < 0 || sample_begin + (long long)sample_count > Nn) return fail(NVWN_EINVAL, "nvwn_cond_producer_run: sample range outside num_frames * stride");
+    if (first_sample < 0 || first_sample + (long long)sample_begin + sample_count > e->N) return fail(NVWN_EINVAL, "nvwn_cond_producer_run: samples do not fit the engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per = (size_t)e->L * e->B * 2 * e->R;
+    const size_t n_feat = (size_t)e->B * C * T, n_wu = (size_t)C * C * K, n_wc = (size_t)e->L * 2 * e->R * C, n_bc = (size_t)e->L * 2 * e->R;
+    float* d_feat = e->cp_scratch; float* d_wut = d_feat + n_feat + n_wu; float* d_bu = d_wut + n_wu;
+    float* d_wc = d_bu + C; float* d_bc = d_wc + n_wc; float* d_u = d_bc + n_bc;
+    float* d_out = d_u + (size_t)e->B * chunk * C;
+    d_out += (4 - ((size_t)(d_out - e->cp_scratch) & 3)) & 3;                 // 16-byte aligned rows for the tiled projection's float4 stores
+    cudaError_t ce = cudaSuccess;
     int rc = 0;
-    for (long long done = 0; done < Nn && ce == cudaSuccess && rc == 0; done += chunk) {
-        const int m = (int)((Nn - done < chunk) ? Nn - done : chunk);
+    for (long long done = sample_begin; done < sample_begin + (long long)sample_count && ce == cudaSuccess && rc == 0; done += chunk) {
+        const long long left = sample_begin + (long long)sample_count - done;
+        const int m = (int)(left < chunk ? left : chunk);
         ce = wn_cond_produce(d_out, d_u, d_feat, d_wut, d_bu, d_wc, d_bc, e->B, C, T, K, stride, e->L, e->R, (int)done, m, st);
         if (ce == cudaSuccess) rc = nvwn_set_conditioning(e, d_out, first_sample + (int)done, m, stream);      // device source: converted in place, stream-ordered
     }
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);                   // the scratch is freed below
-    cudaFree(scratch);
-    if (ce != cudaSuccess) return fail((int)ce, std::string("nvwn_set_conditioning_from_features: ") + cudaGetErrorString(ce));
+    if (ce != cudaSuccess) return fail((int)ce, std::string("nvwn_cond_producer_run: ") + cudaGetErrorString(ce));
     return rc;
+}
+
+int nvwn_set_conditioning_from_features(nvwn_engine* e, const float* features, int n_cond_channels, int num_frames,
+                                        const float* upsample_weight, const float* upsample_bias, int window, int stride,
+                                        const float* cond_weight, const float* cond_bias, int first_sample, void* stream)
+{
+    if (!e) return fail(NVWN_EINVAL, "nvwn_set_conditioning_from_features: NULL argument");
+    const long long Nn = (long long)num_frames * stride;
+    if (first_sample < 0 || (num_frames >= 1 && stride >= 1 && first_sample + Nn > e->N)) return fail(NVWN_EINVAL, "nvwn_set_conditioning_from_features: num_frames * stride samples do not fit the engine");
+    int rc = nvwn_cond_producer_load(e, features, n_cond_channels, num_frames, upsample_weight, upsample_bias, window, stride, cond_weight, cond_bias, stream);
+    if (rc != 0) return rc;
+    rc = nvwn_cond_producer_run(e, first_sample, 0, (int)Nn, stream);
+    if (rc != 0) return rc;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));                        // "returns after the work has completed"
+    return 0;
 }
 
 int nvwn_reset_history(nvwn_engine* e)

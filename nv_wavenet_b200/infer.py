@@ -118,6 +118,23 @@ class NVWavenetInfer:
                                                           _stream(stream)), "setConditioningFromFeatures")
         return T * stride
 
+    def cond_producer_load(self, features, upsample_weight, upsample_bias, cond_weight, cond_bias, stride, stream=None):
+        """First half of set_conditioning_from_features: copies the features and both layers' weights into engine-owned device
+        memory.  Returns the number of samples the sequence covers (T * stride)."""
+        shp = lambda a: tuple(a.shape)
+        B, Cc, T = shp(features)
+        assert B == self.B and shp(upsample_weight)[:2] == (Cc, Cc) and shp(cond_weight)[:2] == (self.L * 2 * self.R, Cc)
+        window = shp(upsample_weight)[2]
+        f, k1 = _ptr(features, np.float32); wu, k2 = _ptr(upsample_weight, np.float32); bu, k3 = _ptr(upsample_bias, np.float32)
+        wc, k4 = _ptr(cond_weight, np.float32); bc, k5 = _ptr(cond_bias, np.float32)
+        check(self._l.nvwn_cond_producer_load(self._h, f, Cc, T, wu, bu, window, stride, wc, bc, _stream(stream)), "condProducerLoad")
+        return T * stride
+
+    def cond_producer_run(self, sample_begin, sample_count, first_sample=0, stream=None):
+        """Second half: conditioning of samples [sample_begin, sample_begin + sample_count) of the loaded sequence, asynchronously on
+        `stream` (record an event after it and make the generating stream wait for it)."""
+        check(self._l.nvwn_cond_producer_run(self._h, first_sample, sample_begin, sample_count, _stream(stream)), "condProducerRun")
+
     def reset_history(self):
         check(self._l.nvwn_reset_history(self._h), "resetHistory")
 

@@ -85,3 +85,48 @@ def test_out_of_range_is_rejected():
     with pytest.raises(Exception):
         e.set_conditioning_from_features(z, np.zeros((3, 3, 8), np.float32), np.zeros(3, np.float32), np.zeros((2 * 2 * 64, 3), np.float32),
                                          np.zeros(2 * 2 * 64, np.float32), 4)        # 5 * 4 = 20 samples > 16
+
+
+def test_producer_ranges_on_a_side_stream_equal_the_one_shot_call_and_the_host_arithmetic():
+    """nvwn_cond_producer_load + _run over three unequal sample ranges on a second stream (the overlapped pipeline of bench.py) must
+    leave the same store as the one-shot call; and the fp32 store must equal the host restatement of the same arithmetic BIT FOR BIT
+    (the register-tiled projection kernel keeps the element function's accumulation order).  Shape: two ragged 128-row tiles, odd L."""
+    import torch
+    import nv_wavenet_b200 as nw
+    from nv_wavenet_b200 import _lib
+    rng = np.random.default_rng(11)
+    L, R, B = 5, 64, 19
+    Cc, T, window, stride = 80, 7, 32, 8                         # 56 samples: 56 x 19 = 1064 rows = 8 full + 1 ragged 128-row tile
+    N = T * stride + 3
+    first = 3
+    g = {"x_features": rng.standard_normal((B, Cc, T)).astype(np.float32),
+         "x_upsample_weight": (0.1 * rng.standard_normal((Cc, Cc, window))).astype(np.float32),
+         "x_upsample_bias": (0.1 * rng.standard_normal(Cc)).astype(np.float32),
+         "x_cond_weight": (0.1 * rng.standard_normal((L * 2 * R, Cc))).astype(np.float32),
+         "x_cond_bias": (0.1 * rng.standard_normal(L * 2 * R)).astype(np.float32),
+         "x_geometry": np.array([Cc, T, window, stride, L, R, B])}
+    want = host_cond(g, "x")                                     # nvwn_cond_from_features_host
+    lib = _lib.lib()
+    lib.nvwn_debug_get_conditioning.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    n = T * stride
+
+    def store(e):
+        got = np.full((n, L, B, 2 * R), np.nan, np.float32)
+        assert lib.nvwn_debug_get_conditioning(e._h, C.c_void_p(got.ctypes.data), first, n) == 0
+        return got
+
+    args = (g["x_features"], g["x_upsample_weight"], g["x_upsample_bias"], g["x_cond_weight"], g["x_cond_bias"], stride)
+    e1 = nw.NVWavenetInfer(L, 2, B, N, R=R, S=256, A=256, dtype=nw.FP32)
+    assert e1.set_conditioning_from_features(*args, first_sample=first) == n
+    one_shot = store(e1)
+    assert np.array_equal(one_shot.view(np.uint32), want.view(np.uint32)), np.abs(one_shot - want).max()
+
+    e2 = nw.NVWavenetInfer(L, 2, B, N, R=R, S=256, A=256, dtype=nw.FP32)
+    side = torch.cuda.Stream()
+    assert e2.cond_producer_load(*args) == n
+    for begin, count in ((0, 17), (17, 1), (18, n - 18)):
+        e2.cond_producer_run(begin, count, first_sample=first, stream=side)
+    side.synchronize()
+    assert np.array_equal(store(e2).view(np.uint32), one_shot.view(np.uint32))
+    with pytest.raises(Exception):
+        e2.cond_producer_run(n - 2, 3, first_sample=first)       # past the loaded sequence
