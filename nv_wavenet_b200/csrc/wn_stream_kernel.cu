@@ -15,8 +15,15 @@
 //     formulas (oracle/wavenet_oracle.c, PORTABLE mode) gives identical bits.
 //   * fp16 storage (TD=__half): weights / Lh / ring in fp16, GEMM inputs rounded to fp16, fp32 FMA
 //     accumulate, fast MUFU transcendentals.  Fallback for shapes the tensor-core kernel does not cover.
+//
+// RING = true (fp32, A <= threads): the weights do not come through per-thread L2 loads but through a shared-memory ring of
+// bulk-TMA pieces (cp.async.bulk + mbarrier complete_tx), issued by one lane of an extra warp in exactly the order the stages
+// consume them: per layer the column slabs [Wprev | Wcur] of stage 1 and [Wres | Wskip] of stage 3, per sample the slabs of Wzs
+// and Wza.  A slab of a column-major matrix is contiguous, so every piece is one or two plain 1-D copies; a thread reads its row
+// of the slab with conflict-free 4-byte shared loads.  The arithmetic and its order are untouched (same bits).
 #include "wn_common.h"
 #include "wn_math.cuh"
+#include "wn_sm100.cuh"
 
 #include <type_traits>
 
@@ -107,7 +114,52 @@ __device__ __forceinline__ void dot_cols(const TD* __restrict__ W, int M, int K,
     }
 }
 
+// the same sum continued over one column slab held in shared memory: ws[k * M + row], k < KS; xs points at column k0 of the inputs
+// (MC = M when it is a compile-time constant: the shared loads then carry immediate offsets)
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <int BT, int KS, int MC, bool FAST, typename N>
+__device__ __forceinline__ void dot_slab(const float* __restrict__ ws, int Mrt, int row, const float* __restrict__ xs, int K,
+                                         float (&acc)[BT], float (&odd)[BT])
+{
+    const int M = MC ? MC : Mrt;
+    const uint32_t wp = sm100::smem_u32(ws + row);
+#pragma unroll
+    for (int j = 0; j < KS; j += 4) {
+        const float w0 = lds_f32(wp + (j + 0) * M * 4), w1 = lds_f32(wp + (j + 1) * M * 4), w2 = lds_f32(wp + (j + 2) * M * 4), w3 = lds_f32(wp + (j + 3) * M * 4);
+#pragma unroll
+        for (int b = 0; b < BT; b++) {
+            const float4 xa = *reinterpret_cast<const float4*>(xs + b * K + j);
+            if (N::exact) {
+                float a = acc[b];
+                a = N::mac(a, w0, xa.x); a = N::mac(a, w1, xa.y); a = N::mac(a, w2, xa.z); a = N::mac(a, w3, xa.w);
+                acc[b] = a;
+            } else {
+                float a = acc[b], o = odd[b];
+                a = N::mac(a, w0, xa.x); o = N::mac(o, w1, xa.y); a = N::mac(a, w2, xa.z); o = N::mac(o, w3, xa.w);
+                acc[b] = a; odd[b] = o;
+            }
+        }
+    }
+}
+
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+
+// geometry of the weight ring (RING kernels): slab widths so that a piece stays at or below 40 KB
+template <int R, int S> struct RingCfg {
+    static constexpr int PIECE = 40960, SLOTS = 4;
+    static constexpr int pow2_le(int v) { int k = 4; while (2 * k <= v) k *= 2; return k; }
+    static constexpr int KS1 = cmin(cmin(R, 32), pow2_le(PIECE / (4 * R * 4)));      // [Wprev | Wcur]: 4R rows of floats per column
+    static constexpr int KS3 = cmin(cmin(R, 32), pow2_le(PIECE / ((R + S) * 4)));    // [Wres | Wskip]: R + S rows per column
+    static constexpr int NS1 = R / KS1, NS3 = R / KS3;
+    static_assert(KS1 >= 4 && KS3 >= 4 && R % KS1 == 0 && R % KS3 == 0 && (R + S) * KS3 * 4 <= PIECE && 4 * R * KS1 * 4 <= PIECE, "piece geometry");
+    static __host__ __device__ int kso(int A) { int k = 32; while (k > 4 && A * k * 4 > PIECE) k >>= 1; return k; }   // output layers: A rows per column
+};
 
 template <int R, int S> struct Shape {
     static constexpr int NT = cmax(cmax(4 * R, R + S), 128);       // threads per CTA
@@ -119,10 +171,12 @@ __host__ __device__ constexpr size_t stream_smem_floats(int A, int L)
     return (size_t)BT * (3 * R + 4 * R + R + 2 * S + 3 * A) + BT * 4 + BT * 2 + L + 4;
 }
 
-template <typename TD, int R, int S, int BT, bool FAST>
-__global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnParams p)
+template <typename TD, int R, int S, int BT, bool FAST, bool RING>
+__global__ void __launch_bounds__(Shape<R, S>::NT + (RING ? 32 : 0), 1) wn_stream_kernel(const WnParams p)
 {
     using N = typename NumSel<TD, FAST>::type;
+    using RC = RingCfg<R, S>;
+    static_assert(!RING || std::is_same<TD, float>::value, "the weight ring is the fp32 kernels'");
     constexpr int NT = Shape<R, S>::NT;
     constexpr int NACT = 2 * R * BT;
     constexpr int ACT_PER = (NACT + NT - 1) / NT;
@@ -149,6 +203,12 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
     float* red = ex + BT * A;              // [BT][4]   max, sum
     int* ysm = reinterpret_cast<int*>(red + BT * 4);   // [BT][2]  yPrev, yCur
     int* dil = ysm + BT * 2;               // [L]
+    // RING: [SLOTS] pieces, 128-byte aligned behind the activations, then full[SLOTS] / empty[SLOTS] barriers
+    float* ring_w = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dil + L + 4) + 127) & ~uintptr_t(127));
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring_w + RC::SLOTS * (RC::PIECE / 4));
+    uint64_t* bar_empty = bar_full + RC::SLOTS;
+    // all compute threads (the producer warp of the RING kernels is not among them)
+    auto SYNC = [&]() { if (RING) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); else __syncthreads(); };
 
     const TD* embPrev = static_cast<const TD*>(p.embPrev);
     const TD* embCur = static_cast<const TD*>(p.embCur);
@@ -172,7 +232,54 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
         for (int l = 0; l < L; l++) { dil[l] = d; d <<= 1; if (d > p.maxDil) d = 1; }
     }
     if (tid < BT) { ysm[tid * 2] = p.yPrev[b0 + tid]; ysm[tid * 2 + 1] = p.yCur[b0 + tid]; }
+    if (RING && tid == 0) {
+        for (int i = 0; i < RC::SLOTS; i++) { sm100::mbar_init(bar_full + i, 1); sm100::mbar_init(bar_empty + i, NT / 32); }
+        sm100::fence_mbar_init();
+    }
     __syncthreads();
+
+    const int kso = RC::kso(A);
+    if (RING && tid >= NT) {
+        // ---- producer warp: one lane streams the pieces in consumption order ----
+        if (tid == NT) {
+            const float* fWprev = reinterpret_cast<const float*>(p.Wprev); const float* fWcur = reinterpret_cast<const float*>(p.Wcur);
+            const float* fWres = reinterpret_cast<const float*>(p.Wres); const float* fWskip = reinterpret_cast<const float*>(p.Wskip);
+            const float* fWzs = reinterpret_cast<const float*>(p.Wzs); const float* fWza = reinterpret_cast<const float*>(p.Wza);
+            uint32_t n = 0;
+            auto put = [&](const float* s0, uint32_t f0, const float* s1, uint32_t f1) {       // floats of the one or two parts of a piece
+                const uint32_t sl = n % RC::SLOTS;
+                sm100::mbar_wait(bar_empty + sl, ((n / RC::SLOTS) & 1) ^ 1);
+                sm100::mbar_arrive_expect_tx(bar_full + sl, (f0 + f1) * 4);
+                float* dst = ring_w + sl * (RC::PIECE / 4);
+                sm100::tma_load_1d(dst, s0, f0 * 4, bar_full + sl);
+                if (f1) sm100::tma_load_1d(dst + f0, s1, f1 * 4, bar_full + sl);
+                n++;
+            };
+            for (int t = p.init_sample; t < p.init_sample + p.count; t++) {
+                for (int l = 0; l < L; l++) {
+                    for (int j = 0; j < RC::NS1; j++)
+                        put(fWprev + (size_t)l * 2 * R * R + (size_t)j * RC::KS1 * 2 * R, 2 * R * RC::KS1, fWcur + (size_t)l * 2 * R * R + (size_t)j * RC::KS1 * 2 * R, 2 * R * RC::KS1);
+                    for (int j = 0; j < RC::NS3; j++)
+                        put(fWres + (size_t)l * R * R + (size_t)j * RC::KS3 * R, R * RC::KS3, fWskip + (size_t)l * S * R + (size_t)j * RC::KS3 * S, S * RC::KS3);
+                }
+                for (int j = 0; j < S / kso; j++) put(fWzs + (size_t)j * kso * A, (uint32_t)(A * kso), nullptr, 0);
+                for (int j = 0; j < A / kso; j++) put(fWza + (size_t)j * kso * A, (uint32_t)(A * kso), nullptr, 0);
+            }
+        }
+        return;
+    }
+    // consumer side of the ring: every compute warp takes every piece (whether or not its threads have rows in that stage)
+    uint32_t pcn = 0;
+    auto piece_wait = [&]() -> const float* {
+        const uint32_t sl = pcn % RC::SLOTS;
+        sm100::mbar_wait(bar_full + sl, (pcn / RC::SLOTS) & 1);
+        return ring_w + sl * (RC::PIECE / 4);
+    };
+    auto piece_done = [&]() {
+        __syncwarp();
+        if ((tid & 31) == 0) sm100::mbar_arrive(bar_empty + pcn % RC::SLOTS);
+        pcn++;
+    };
 
     // fixed per-thread roles
     const bool has_x = tid < R * BT;
@@ -214,7 +321,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
             xp[xb * R + xr] = xp_nxt;
         }
         for (int i = tid; i < S * BT; i += NT) skip[i] = 0.f;     // zero matrix (reference.cpp:290)
-        __syncthreads();
+        SYNC();
 
         for (int l = 0; l < L; l++) {
             // ---- conditioning / history prefetch for the next layer (or layer 0 of the next sample) ----
@@ -238,7 +345,24 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
             }
 
             // ---- stage 1: a_prev = Wprev.x[t-d], a_cur = Wcur.x[t]  (reference.cpp:61-65) ----
-            if (tid < 4 * R) {
+            if (RING) {
+                const bool cur = tid >= 2 * R;
+                const int row = cur ? tid - 2 * R : tid;
+                float acc[BT], odd[BT];
+#pragma unroll
+                for (int b = 0; b < BT; b++) { acc[b] = 0.f; odd[b] = 0.f; }
+                for (int j = 0; j < RC::NS1; j++) {
+                    const float* pw = piece_wait();
+                    if (tid < 4 * R)
+                        dot_slab<BT, RC::KS1, 2 * R, FAST, N>(pw + (cur ? 2 * R * RC::KS1 : 0), 2 * R, row, (cur ? xq : xp) + j * RC::KS1, R, acc, odd);
+                    piece_done();
+                }
+                if (tid < 4 * R) {
+                    float* dst = cur ? ac : ap;
+#pragma unroll
+                    for (int b = 0; b < BT; b++) dst[b * 2 * R + row] = N::exact ? acc[b] : acc[b] + odd[b];
+                }
+            } else if (tid < 4 * R) {
                 const bool cur = tid >= 2 * R;
                 const int row = cur ? tid - 2 * R : tid;
                 const TD* W = (cur ? Wcur : Wprev) + (size_t)l * 2 * R * R;
@@ -248,7 +372,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
 #pragma unroll
                 for (int b = 0; b < BT; b++) dst[b * 2 * R + row] = acc[b];
             }
-            __syncthreads();
+            SYNC();
 
             // ---- pre-activation adds and tanh / sigmoid (reference.cpp:67-72, 76-78) ----
 #pragma unroll
@@ -262,7 +386,7 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
                     ac[idx] = (row < R) ? N::tanh_(v) : N::sigmoid_(v);
                 }
             }
-            __syncthreads();
+            SYNC();
 
             // ---- h = tanh * sigmoid; stage-1 inputs are dead, install x[t-d] of the next layer ----
             if (has_x) {
@@ -270,16 +394,33 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
                 hq[xb * R + xr] = N::q(h);
                 xp[xb * R + xr] = xp_nxt;
             }
-            __syncthreads();
+            SYNC();
 
             // ---- stage 3: residual (reference.cpp:82-84) and skip (reference.cpp:86-90) ----
+            float acc[BT];
+            if (RING) {
+                const bool is_res = tid < R;
+                const int row = is_res ? tid : tid - R;
+                float odd[BT];
+#pragma unroll
+                for (int b = 0; b < BT; b++) { acc[b] = 0.f; odd[b] = 0.f; }
+                for (int j = 0; j < RC::NS3; j++) {
+                    const float* pw = piece_wait();
+                    if (tid < R) dot_slab<BT, RC::KS3, R, FAST, N>(pw, R, row, hq + j * RC::KS3, R, acc, odd);
+                    else if (tid < R + S) dot_slab<BT, RC::KS3, S, FAST, N>(pw + R * RC::KS3, S, row, hq + j * RC::KS3, R, acc, odd);
+                    piece_done();
+                }
+                if (!N::exact) {
+#pragma unroll
+                    for (int b = 0; b < BT; b++) acc[b] += odd[b];
+                }
+            }
             if (tid < R + S) {
                 const bool is_res = tid < R;
                 const int row = is_res ? tid : tid - R;
                 const TD* W = is_res ? Wres + (size_t)l * R * R : Wskip + (size_t)l * S * R;
                 const float bias = is_res ? N::ld(Bres + (size_t)l * R + row) : N::ld(Bskip + (size_t)l * S + row);
-                float acc[BT];
-                dot_cols<TD, BT, KBR, FAST>(W, is_res ? R : S, R, row, hq, acc);
+                if (!RING) dot_cols<TD, BT, KBR, FAST>(W, is_res ? R : S, R, row, hq, acc);
                 if (is_res) {
 #pragma unroll
                     for (int b = 0; b < BT; b++) {
@@ -301,35 +442,64 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
                     }
                 }
             }
-            __syncthreads();
+            SYNC();
         }
 
         // ---- output layers (reference.cpp:93-104) ----
-        for (int row = tid; row < A; row += NT) {
-            float acc[BT];
-            const float bias = N::ld(Bzs + row);
-            dot_cols<TD, BT, 32, FAST>(Wzs, A, S, row, skq, acc);
+        // (RING kernels: A <= NT, one row per thread; the slabs of Wzs, then of Wza, come through the ring)
+        auto out_dot = [&](const TD* W, int K, int row, const float* xs, float (&acc)[BT]) {
+            if (RING) {
+                float odd[BT];
 #pragma unroll
-            for (int b = 0; b < BT; b++) {
-                float v = N::add(acc[b], bias);
-                v = (v < 0.f) ? 0.f : v;
-                zsq[b * A + row] = N::q(v);
-                if (dump) p.Zs[(size_t)(b0 + b) * A + row] = v;
+                for (int b = 0; b < BT; b++) { acc[b] = 0.f; odd[b] = 0.f; }
+                for (int j = 0; j < K / kso; j++) {
+                    const float* pw = piece_wait();
+                    if (row < A) {
+                        if (A == 256 && kso == 32) dot_slab<BT, 32, 256, FAST, N>(pw, A, row, xs + j * 32, K, acc, odd);
+                        else if (kso == 32) dot_slab<BT, 32, 0, FAST, N>(pw, A, row, xs + j * 32, K, acc, odd);
+                        else if (kso == 16) dot_slab<BT, 16, 0, FAST, N>(pw, A, row, xs + j * 16, K, acc, odd);
+                        else if (kso == 8) dot_slab<BT, 8, 0, FAST, N>(pw, A, row, xs + j * 8, K, acc, odd);
+                        else dot_slab<BT, 4, 0, FAST, N>(pw, A, row, xs + j * 4, K, acc, odd);
+                    }
+                    piece_done();
+                }
+                if (!N::exact) {
+#pragma unroll
+                    for (int b = 0; b < BT; b++) acc[b] += odd[b];
+                }
+            } else {
+                dot_cols<TD, BT, 32, FAST>(W, A, K, row, xs, acc);
+            }
+        };
+        for (int row = tid; row < (RING ? NT : A); row += NT) {
+            float acc[BT];
+            out_dot(Wzs, S, row, skq, acc);
+            if (row < A) {
+                const float bias = N::ld(Bzs + row);
+#pragma unroll
+                for (int b = 0; b < BT; b++) {
+                    float v = N::add(acc[b], bias);
+                    v = (v < 0.f) ? 0.f : v;
+                    zsq[b * A + row] = N::q(v);
+                    if (dump) p.Zs[(size_t)(b0 + b) * A + row] = v;
+                }
             }
         }
-        __syncthreads();
-        for (int row = tid; row < A; row += NT) {
+        SYNC();
+        for (int row = tid; row < (RING ? NT : A); row += NT) {
             float acc[BT];
-            const float bias = N::ld(Bza + row);
-            dot_cols<TD, BT, 32, FAST>(Wza, A, A, row, zsq, acc);
+            out_dot(Wza, A, row, zsq, acc);
+            if (row < A) {
+                const float bias = N::ld(Bza + row);
 #pragma unroll
-            for (int b = 0; b < BT; b++) {
-                const float v = N::add(acc[b], bias);
-                za[b * A + row] = v;
-                if (dump) p.Za[(size_t)(b0 + b) * A + row] = v;
+                for (int b = 0; b < BT; b++) {
+                    const float v = N::add(acc[b], bias);
+                    za[b * A + row] = v;
+                    if (dump) p.Za[(size_t)(b0 + b) * A + row] = v;
+                }
             }
         }
-        __syncthreads();
+        SYNC();
 
         // ---- softmax + categorical sample ----
         const int warp = tid >> 5, lane = tid & 31;
@@ -342,9 +512,9 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
                 for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 if (lane == 0) red[warp * 4] = mx;
             }
-            __syncthreads();
+            SYNC();
             for (int i = tid; i < A * BT; i += NT) ex[i] = wn::expf_portable(__fsub_rn(za[i], red[(i / A) * 4]));
-            __syncthreads();
+            SYNC();
             if (tid < BT) {
                 float s = 0.f;
                 const float* e = ex + tid * A;
@@ -354,13 +524,13 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
                 }
                 red[tid * 4 + 1] = s;
             }
-            __syncthreads();
+            SYNC();
             for (int i = tid; i < A * BT; i += NT) {
                 const float pr = __fdiv_rn(ex[i], red[(i / A) * 4 + 1]);
                 ex[i] = pr;
                 if (dump) p.P[(size_t)(b0 + i / A) * A + (i % A)] = pr;
             }
-            __syncthreads();
+            SYNC();
             if (tid < BT) {
                 const float sel = p.sel[(size_t)t * B + b0 + tid];
                 const float* pr = ex + tid * A;
@@ -426,24 +596,42 @@ __global__ void __launch_bounds__(Shape<R, S>::NT, 1) wn_stream_kernel(const WnP
                 }
             }
         }
-        __syncthreads();
+        SYNC();
     }
 
     if (tid < BT) { p.yPrev[b0 + tid] = ysm[tid * 2]; p.yCur[b0 + tid] = ysm[tid * 2 + 1]; }
 }
 
+template <typename TD, int R, int S, int BT, bool FAST, bool RING>
+cudaError_t launch_kernel(const WnParams& p, cudaStream_t stream, WnLaunchInfo* info)
+{
+    constexpr int NT = Shape<R, S>::NT;
+    using RC = RingCfg<R, S>;
+    size_t smem = stream_smem_floats<R, S, BT>(p.A, p.L) * sizeof(float);
+    if (RING) smem += 128 + (size_t)RC::SLOTS * RC::PIECE + 2 * RC::SLOTS * sizeof(uint64_t);
+    auto kfn = wn_stream_kernel<TD, R, S, BT, FAST, RING>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = p.B / BT, block = NT + (RING ? 32 : 0);
+    kfn<<<grid, block, smem, stream>>>(p);
+    if (info) { info->grid = grid; info->block = block; info->smem_bytes = (int)smem; info->batch_per_cta = BT; info->cluster = 1; }
+    return cudaGetLastError();
+}
+
+// fp32: weights through the shared-memory ring when the output layers fit one row per thread and every matrix starts on a
+// 16-byte boundary (bulk copies); NVWN_STREAM_RING=0 keeps the per-thread L2 loads
 template <typename TD, int R, int S, int BT, bool FAST>
 cudaError_t launch_one(const WnParams& p, cudaStream_t stream, WnLaunchInfo* info)
 {
-    constexpr int NT = Shape<R, S>::NT;
-    const size_t smem = stream_smem_floats<R, S, BT>(p.A, p.L) * sizeof(float);
-    auto kfn = wn_stream_kernel<TD, R, S, BT, FAST>;
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int grid = p.B / BT;
-    kfn<<<grid, NT, smem, stream>>>(p);
-    if (info) { info->grid = grid; info->block = NT; info->smem_bytes = (int)smem; info->batch_per_cta = BT; info->cluster = 1; }
-    return cudaGetLastError();
+    if constexpr (std::is_same<TD, float>::value) {
+        static const bool want = [] { const char* v = getenv("NVWN_STREAM_RING"); return !v || atoi(v) != 0; }();
+        const void* mats[] = {p.Wprev, p.Wcur, p.Wres, p.Wskip, p.Wzs, p.Wza};
+        bool ok = want && R <= 64 && p.A <= Shape<R, S>::NT && p.A % 32 == 0;       // (R = 128: measured slower than the per-thread loads)
+        for (const void* m : mats) ok = ok && (reinterpret_cast<uintptr_t>(m) & 15) == 0;
+        const size_t smem = stream_smem_floats<R, S, BT>(p.A, p.L) * sizeof(float) + 128 + (size_t)RingCfg<R, S>::SLOTS * RingCfg<R, S>::PIECE + 64;
+        if (ok && smem <= 232448) return launch_kernel<TD, R, S, BT, FAST, true>(p, stream, info);
+    }
+    return launch_kernel<TD, R, S, BT, FAST, false>(p, stream, info);
 }
 
 template <typename TD, int R, int S, bool FAST>
