@@ -623,10 +623,10 @@ cudaError_t launch_kernel(const WnParams& p, cudaStream_t stream, WnLaunchInfo* 
 template <typename TD, int R, int S, int BT, bool FAST>
 cudaError_t launch_one(const WnParams& p, cudaStream_t stream, WnLaunchInfo* info)
 {
-    if constexpr (std::is_same<TD, float>::value) {
+    if constexpr (std::is_same<TD, float>::value && R <= 64) {                 // (R = 128: measured slower than the per-thread loads)
         static const bool want = [] { const char* v = getenv("NVWN_STREAM_RING"); return !v || atoi(v) != 0; }();
         const void* mats[] = {p.Wprev, p.Wcur, p.Wres, p.Wskip, p.Wzs, p.Wza};
-        bool ok = want && R <= 64 && p.A <= Shape<R, S>::NT && p.A % 32 == 0;       // (R = 128: measured slower than the per-thread loads)
+        bool ok = want && p.A <= Shape<R, S>::NT && p.A % 32 == 0;
         for (const void* m : mats) ok = ok && (reinterpret_cast<uintptr_t>(m) & 15) == 0;
         const size_t smem = stream_smem_floats<R, S, BT>(p.A, p.L) * sizeof(float) + 128 + (size_t)RingCfg<R, S>::SLOTS * RingCfg<R, S>::PIECE + 64;
         if (ok && smem <= 232448) return launch_kernel<TD, R, S, BT, FAST, true>(p, stream, info);
