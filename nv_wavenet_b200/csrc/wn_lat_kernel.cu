@@ -49,7 +49,6 @@ struct Cfg {
     //   P1 = [ Wcur_l | Wprev_{(l+1) mod L} ]  (32 KB)      P2 = [ Wres_l | Wskip_l ]  (8 KB + S x 128 B)
     static constexpr int W_CUR = 0, W_PREV = 16384, W_RES = 32768, W_SKIP = 40960;
     static constexpr int P1_BYTES = 32768, P2_BYTES = 8192 + S * 128;
-    static constexpr int LAYER_BYTES = P1_BYTES + P2_BYTES;
     // output GEMMs: 4 + 4 ring pieces per sample, each all 32 n-tiles x OJP k-step pairs
     static constexpr int NQ_ZS = 4, NQ_ZA = 4;
     static constexpr int OJP_ZS = S / 128, OJP_ZA = A / 128;         // k-step pairs per piece
@@ -132,13 +131,6 @@ __device__ __forceinline__ void load_a(uint32_t (&a)[4], uint32_t addr)
 {
     const uint4 v = lds128(addr);
     a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-}
-// global loads of data written earlier by this CTA (history ring): L2 only
-__device__ __forceinline__ uint4 ldg_cg_v4(const void* p)
-{
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
 }
 // predicated load into an existing register quad: no select on the loaded value, so nothing waits for the load here
 __device__ __forceinline__ void ldg_nc_v4_if(uint4& d, const void* p, bool pred)
