@@ -20,6 +20,9 @@
 //                   refilled as soon as its occupant is consumed -- each piece is in flight two layers before its use.
 //   Lh (the only HBM stream), biases and the dilated history x[t-d] are prefetched into registers one / two layers ahead.
 //
+// wn_lat2_kernel (second half of this file, the default up to ~720 utterances) spreads the same data flow over a cluster of three
+// CTAs per tile -- chain / tail / prep -- that hand tiles over through distributed shared memory; see the comment there.
+//
 // Replaces nv_wavenet_{singleblock,dualblock,persistent}.cuh + matrix_math.cuh + softmax.cuh of the reference for
 // T_data = half while the batch is small enough to be latency-bound.  Numerical contract: oracle/wavenet_oracle.c
 // WNO_PREC_FP16 (GEMM inputs fp16, fp32 accumulation, fp32 residual stream / skip sum / softmax), gate evaluated with
@@ -813,10 +816,10 @@ __global__ void __launch_bounds__(NT, 1) wn_lat_kernel(const WnParams p, const u
 #undef TRACE
 }
 
-// ================================================================================================ two-CTA cluster variant
+// ================================================================================================ three-CTA cluster variant
 // The single-CTA kernel above runs at ~83 % of its SM's shared-memory bandwidth (per layer step: 72 KB written by TMA, 72 KB of
 // B fragments and 48 KB of A fragments read back; ncu: 0.57 LSU wavefronts per cycle + the TMA writes).  Here one 16-utterance tile
-// is served by a CLUSTER OF TWO CTAs on two SMs, which halves that traffic per SM:
+// is served by a CLUSTER OF THREE CTAs on three SMs, and only what depends on the previous sample stays on the first one:
 //   rank 0 "chain": embedding, cur / res GEMMs, gate, history ring writes             ring pieces [Wcur_l | Wres_l] (24 KB)
 //   rank 1 "tail":  skip GEMM of every step (off the chain), Zs, Za, softmax, sampling ring pieces Wskip_l and the output pieces
 //   rank 2 "prep":  (Bh + Lh) + Wprev . x[t-d] of the steps to come, up to NAP ahead   ring pieces Wprev_l (16 KB)
