@@ -211,7 +211,7 @@ def _select_fp16_kernel(kernel, monkeypatch):
         monkeypatch.delenv(k, raising=False)
     if kernel == "stream":
         monkeypatch.setenv("NVWN_FP16_KERNEL", "stream")
-    elif kernel == "lat":                          # latency-mode kernel (mma.sync, 16-utterance tiles, a three-CTA cluster per tile up to 784 utterances): AUTO up to 2368 utterances
+    elif kernel == "lat":                          # latency-mode kernel (mma.sync, 16-utterance tiles, a three-CTA cluster per tile while all clusters are resident, 720 utterances): AUTO up to 2368 utterances
         monkeypatch.setenv("NVWN_FP16_KERNEL", "lat")
     elif kernel == "lat_single":                   # ... one CTA per tile: what AUTO uses from 1185 to 2368 utterances
         monkeypatch.setenv("NVWN_FP16_KERNEL", "lat"); monkeypatch.setenv("NVWN_LAT_CLUSTER", "0")
