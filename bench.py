@@ -482,8 +482,9 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     alg = algorithmic_bytes(L, R, S, A, T)
     achieved = B * N * alg / (kernel_ms * 1e-3) / 1e9                # one launch = one step of one GPU
-    # DRAM traffic is not measured on this run: the committed ncu capture (profiles/ncu_summary.json) gives bytes per unit
-    # for a shorter launch of the same kernel; the figure scaled to this launch is reported as an extrapolation
+    # DRAM traffic cannot be measured on this run (no profiler in a timed run): `traffic` is dram read + written of the committed
+    # `ncu --set full` capture (profiles/ncu_summary.json) when that capture is of exactly this launch (same config, kernel, batch and
+    # sample count), else null; `traffic_extrapolated` scales the capture's bytes per unit to this launch in any case
     kname = {16: "wn_stream_kernel", 17: "wn_tc_kernel", 18: "wn_lat2_kernel" if info["cluster"] > 1 else "wn_lat_kernel"}.get(info["kernel"], str(info["kernel"]))
     traffic = None                                  # DRAM bytes of one launch of this very shape, if the committed ncu capture is of it
     traffic_x = None
